@@ -1,0 +1,138 @@
+/*
+ * Flat C facade over the public `evolver` API -- see cupss_capi.h.
+ * Compiled against EITHER this repo's inc/cupss.h (product) OR the reference's
+ * (oracle build); only public members/methods are used
+ * (/root/reference/inc/cupss/evolver.h:31-85, inc/cupss/field.h:47-106,
+ *  inc/cupss/term.h:38-60).
+ */
+#include "cupss_capi.h"
+
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "cupss.h"
+
+static evolver *EV(void *p) { return static_cast<evolver *>(p); }
+
+extern "C" {
+
+void *cupss_capi_create(int with_cuda, int sx, int sy, int sz, float dx, float dy, float dz, float dt, int write_every)
+{
+    bool dev = with_cuda ? RUN_GPU : RUN_CPU;
+    /* the three public constructors fix the dimension (evolver.h:31-33) */
+    if (sz == 1 && sy == 1) return new evolver(dev, sx, dx, dt, write_every);
+    if (sz == 1) return new evolver(dev, sx, sy, dx, dy, dt, write_every);
+    return new evolver(dev, sx, sy, sz, dx, dy, dz, dt, write_every);
+}
+
+void cupss_capi_destroy(void *ev) { delete EV(ev); }
+
+int cupss_capi_create_field(void *ev, const char *name, int dynamic) { return EV(ev)->createField(name, dynamic != 0); }
+int cupss_capi_add_parameter(void *ev, const char *name, float value) { return EV(ev)->addParameter(name, value); }
+int cupss_capi_add_equation(void *ev, const char *equation) { return EV(ev)->addEquation(equation); }
+int cupss_capi_add_noise(void *ev, const char *field, const char *expr) { return EV(ev)->addNoise(field, expr); }
+
+int cupss_capi_create_term(void *ev, const char *field, const cupss_capi_pres *p, int npres, const char *const *product, int nproduct)
+{
+    std::vector<pres> pv;
+    for (int i = 0; i < npres; i++) {
+        pres q;
+        q.preFactor = p[i].preFactor; q.q2n = p[i].q2n; q.iqx = p[i].iqx;
+        q.iqy = p[i].iqy; q.iqz = p[i].iqz; q.invq = p[i].invq;
+        pv.push_back(q);
+    }
+    std::vector<std::string> prod;
+    for (int i = 0; i < nproduct; i++) prod.push_back(product[i]);
+    return EV(ev)->createTerm(field, pv, prod);
+}
+
+int cupss_capi_create_from_file(void *ev, const char *path) { return EV(ev)->createFromFile(path); }
+void cupss_capi_prepare_problem(void *ev) { EV(ev)->prepareProblem(); }
+
+int cupss_capi_advance_time(void *ev, int nsteps)
+{
+    evolver *e = EV(ev);
+    for (int i = 0; i < nsteps; i++) e->advanceTime();
+    return 0;
+}
+
+void cupss_capi_copy_all_data_to_host(void *ev) { EV(ev)->copyAllDataToHost(); }
+void cupss_capi_write_out(void *ev) { EV(ev)->writeOut(); }
+void cupss_capi_set_output_field(void *ev, const char *name, int on) { EV(ev)->setOutputField(name, on); }
+int cupss_capi_update_parameter(void *ev, const char *name, float value) { return EV(ev)->updateParameter(name, value); }
+float cupss_capi_get_parameter(void *ev, const char *name) { return EV(ev)->getParameter(name); }
+int cupss_capi_get_timestep(void *ev) { return EV(ev)->getCurrentTimestep(); }
+float cupss_capi_get_time(void *ev) { return EV(ev)->getCurrentTime(); }
+void cupss_capi_set_write_precision(void *ev, int digits) { EV(ev)->writePrecision = digits; }
+
+float *cupss_capi_field_real(void *ev, const char *name)
+{
+    evolver *e = EV(ev);
+    if (e->existsField(name) < 0) return nullptr;
+    return reinterpret_cast<float *>(e->fieldsMap[name]->real_array);
+}
+
+float *cupss_capi_field_comp(void *ev, const char *name)
+{
+    evolver *e = EV(ev);
+    if (e->existsField(name) < 0) return nullptr;
+    return reinterpret_cast<float *>(e->fieldsMap[name]->comp_array);
+}
+
+void cupss_capi_initialize_uniform(void *ev, const char *name, float value) { EV(ev)->initializeUniform(name, value); }
+void cupss_capi_initialize_droplet(void *ev, const char *name, float v_out, float v_in, float radius, float width, int cx, int cy, int cz)
+{
+    EV(ev)->initializeDroplet(name, v_out, v_in, radius, width, cx, cy, cz);
+}
+void cupss_capi_add_droplet(void *ev, const char *name, float value, float radius, float width, int cx, int cy, int cz)
+{
+    EV(ev)->addDroplet(name, value, radius, width, cx, cy, cz);
+}
+void cupss_capi_initialize_half_system(void *ev, const char *name, float v1, float v2, float width, int direction)
+{
+    EV(ev)->initializeHalfSystem(name, v1, v2, width, direction);
+}
+void cupss_capi_initialize_from_file(void *ev, const char *name, const char *path, int skiprows, char delimiter)
+{
+    EV(ev)->initializeFromFile(name, path, skiprows, delimiter);
+}
+
+static void put_pres(std::ostringstream &os, const pres &p)
+{
+    char num[64];
+    std::snprintf(num, sizeof num, "%.9g", (double)p.preFactor);
+    os << "{" << num << "," << p.q2n << "," << p.iqx << "," << p.iqy << "," << p.iqz << "," << p.invq << "}";
+}
+
+int cupss_capi_dump_plan(void *ev, char *buf, int buflen)
+{
+    evolver *e = EV(ev);
+    std::ostringstream os;
+    for (size_t f = 0; f < e->fields.size(); f++) {
+        field *F = e->fields[f];
+        os << "field " << F->name << " dynamic=" << (F->dynamic ? 1 : 0)
+           << " alias=" << (F->needsaliasing ? 1 : 0) << " order=" << F->aliasing_order
+           << " noisy=" << (F->isNoisy ? 1 : 0);
+        if (F->isNoisy) { os << " noise="; put_pres(os, F->noise_amplitude); }
+        os << "\n  implicit";
+        for (size_t i = 0; i < F->implicit.size(); i++) { os << " "; put_pres(os, F->implicit[i]); }
+        os << "\n";
+        for (size_t t = 0; t < F->terms.size(); t++) {
+            term *T = F->terms[t];
+            os << "  term";
+            for (size_t i = 0; i < T->prefactors_h.size(); i++) { os << " "; put_pres(os, T->prefactors_h[i]); }
+            os << " (";
+            for (size_t k = 0; k < T->product.size(); k++) os << " " << T->product[k]->name;
+            os << " )\n";
+        }
+    }
+    std::string s = os.str();
+    if ((int)s.size() + 1 > buflen) return -(int)(s.size() + 1);
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+} /* extern "C" */
