@@ -1,0 +1,961 @@
+// engine.cu -- plan object, per-equation fused schedule and the C ABI (include/cupss_b200.h).
+//
+// What evolver::advanceTime (/root/reference/src/evolver.cpp:199-226) does with 4 sweeps of
+// field::updateTerms / field::setRHS, each a chain of un-fused kernels, full C2C cuFFTs and
+// cudaDeviceSynchronize(), is compiled here ONCE (finalize) into a short list of launches:
+//
+//   per sweep class (constraint fields first, then dynamic fields -- the reference's Jacobi order):
+//     x pass      C2R of the dealiased fields, real-space products, R2C          (kernels_x.cu)
+//     y pass      forward, 3-D only                                              (kernels_axis.cu, plain)
+//     [all-to-all over NVLink when the grid is slab-partitioned]
+//     k stage     last forward pass + update of every field of the sweep + dealias + first inverse pass
+//     y pass      inverse, 3-D only
+//
+// Storage (per rank): Hermitian half spectra, complex64, [sz][sy_local][pitch] with pitch =
+// roundup(sx/2+1, 16) so every row is 128-byte aligned; the dealiased real fields exist only as
+// "y-inverse done" half spectra W2 = [sz_local][sy][pitch] which the x pass turns into real lines
+// on chip.  W2 starts at zero, which reproduces the reference's step-0 behaviour (real_dealiased is
+// zero until a field's first setRHS).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cupss_b200.h"
+#include "kernels.h"
+
+using namespace cupss;
+
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(CUPSS_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKR(call)                          \
+    do {                                   \
+        int r_ = (call);                   \
+        if (r_ != CUPSS_B200_OK) return r_; \
+    } while (0)
+
+// ---------------------------------------------------------------- NCCL, bound lazily (the library loads without it)
+struct Id128 { char b[128]; };
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.h) return CUPSS_B200_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail(CUPSS_B200_ERR_COMM, "libnccl.so.2 not found: %s", dlerror());
+#define SYM(field, name)                                                         \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name);                            \
+    if (!g_nccl.field) return fail(CUPSS_B200_ERR_COMM, "NCCL symbol %s missing", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return CUPSS_B200_OK;
+}
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0) return fail(CUPSS_B200_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------- plan data model
+namespace {
+
+struct Pres { float pre; int q2n, iqx, iqy, iqz, invq; };
+struct Term { std::vector<Pres> pres; std::vector<int> product; };
+
+struct Field {
+    std::string name;
+    bool dynamic = false;
+    std::vector<Pres> implicit;
+    std::vector<Term> terms;
+    bool noisy = false;
+    Pres noise{};
+    unsigned long long seed = 0;
+    bool needsAlias = false;
+    int aliasOrder = 1;
+    float2* S = nullptr;    // spectrum
+    float2* W2 = nullptr;   // dealiased field, y-inverse done
+};
+
+struct Launch {
+    enum Kind { XPASS, AXIS_PLAIN, AXIS_KSTAGE, A2A, BUMP } kind;
+    char name[64];
+    int L = 0, dir = 0, mode = 0;
+    AxisArgs ax{};
+    KStageD ks{};
+    XArgs xa{};
+    const float2* send = nullptr;
+    float2* recv = nullptr;
+    size_t chunk = 0;   // float2 per peer
+    double bytes = 0;   // algorithmic HBM bytes (A2A: bytes sent)
+};
+
+int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+}  // namespace
+
+struct cupss_b200_plan {
+    int sx, sy, sz;
+    float dx, dy, dz, dt;
+    int dim;
+    int rank = 0, nranks = 1;
+    int zl, kyl;           // local z planes (real space) / local ky rows (Fourier space)
+    int ncol, pitch;
+    size_t specElems;      // float2 per spectrum-shaped array on this rank
+    int dealiasRule = CUPSS_B200_DEALIAS_GPU_RULE;
+    std::vector<Field> fields;
+    std::vector<Launch> step;
+    std::vector<float2*> scratch;
+    std::map<int, float2*> twiddles;
+    float* realBuf = nullptr;
+    unsigned int* stepCounter = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    bool finalized = false;
+    bool useGraph = true;
+    void* comm = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // ------------------------------------------------------------ helpers
+    int get_twiddle(int L, const float2** out) {
+        auto it = twiddles.find(L);
+        if (it != twiddles.end()) { *out = it->second; return CUPSS_B200_OK; }
+        std::vector<float2> h(L);
+        for (int k = 0; k < L; ++k) {
+            const double a = -2.0 * kPi * (double)k / (double)L;
+            h[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        float2* d = nullptr;
+        CK(cudaMalloc(&d, sizeof(float2) * L));
+        CK(cudaMemcpyAsync(d, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        twiddles[L] = d;
+        *out = d;
+        return CUPSS_B200_OK;
+    }
+    int get_scratch(size_t idx, float2** out) {
+        while (scratch.size() <= idx) scratch.push_back(nullptr);
+        if (!scratch[idx]) {
+            CK(cudaMalloc(&scratch[idx], specElems * sizeof(float2)));
+            CK(cudaMemsetAsync(scratch[idx], 0, specElems * sizeof(float2), stream));
+        }
+        *out = scratch[idx];
+        return CUPSS_B200_OK;
+    }
+    double spec_bytes() const { return (double)ncol * (double)sy * (double)sz / nranks * 8.0; }
+
+    // Addressing of the three kinds of strided pass.
+    void fill_common(AxisArgs& a, int L) {
+        a.ncol = ncol;
+        a.ncolTiles = (ncol + axis_tile_cols(L) - 1) / axis_tile_cols(L);
+        a.sx = sx; a.sy = sy; a.sz = sz;
+        a.maskOn = 0; a.cutx = a.cuty = a.cutz = 0;
+        a.kyBase = rank * kyl;
+    }
+    // last axis of the transform: z in 3-D (rows kz, batch ky_local), y in 2-D, nothing in 1-D
+    int make_last_axis(AxisArgs& a, int* L) {
+        *L = dim == 3 ? sz : (dim == 2 ? sy : 1);
+        fill_common(a, *L);
+        AxisAddr n{};
+        if (dim == 3) { n.bs = pitch; n.rs = (long long)kyl * pitch; a.nbatch = kyl; a.axis = 2; }
+        else if (dim == 2) { n.bs = 0; n.rs = pitch; a.nbatch = 1; a.axis = 1; }
+        else { n.bs = 0; n.rs = 0; a.nbatch = 1; a.axis = 0; }
+        n.cs = 0; n.rpcShift = ilog2(*L); n.rpcMask = *L - 1;
+        a.ain = n; a.aout = n;
+        return get_twiddle(*L, &a.tw);
+    }
+    // y pass of a 3-D transform: natural side [z_local][y][pitch], exchange side [peer][z_local][ky_local][pitch]
+    int make_y_axis(AxisArgs& a, bool forward) {
+        fill_common(a, sy);
+        a.nbatch = zl; a.axis = 1;
+        AxisAddr nat{}, exc{};
+        nat.bs = (long long)sy * pitch; nat.rs = pitch; nat.cs = 0; nat.rpcShift = ilog2(sy); nat.rpcMask = sy - 1;
+        exc.bs = (long long)kyl * pitch; exc.rs = pitch; exc.cs = (long long)zl * kyl * pitch;
+        exc.rpcShift = ilog2(kyl); exc.rpcMask = kyl - 1;
+        if (forward) { a.ain = nat; a.aout = exc; } else { a.ain = exc; a.aout = nat; }
+        return get_twiddle(sy, &a.tw);
+    }
+
+    int add_a2a(std::vector<Launch>& out, const char* nm, const float2* send, float2* recv) {
+        Launch l{};
+        l.kind = Launch::A2A;
+        snprintf(l.name, sizeof l.name, "%s", nm);
+        l.send = send; l.recv = recv;
+        l.chunk = (size_t)zl * kyl * pitch;
+        l.bytes = (double)l.chunk * 8.0 * (nranks - 1);
+        out.push_back(l);
+        return CUPSS_B200_OK;
+    }
+
+    int run_launch(Launch& l) {
+        switch (l.kind) {
+            case Launch::XPASS: CK(launch_xpass(sx, l.mode, l.xa, stream)); break;
+            case Launch::AXIS_PLAIN: CK(launch_axis_plain(l.L, l.dir, l.ax, stream)); break;
+            case Launch::AXIS_KSTAGE: CK(launch_axis_kstage(l.L, l.ax, l.ks, stream)); break;
+            case Launch::BUMP: CK(launch_bump_counter(stepCounter, stream)); break;
+            case Launch::A2A: {
+                NK(g_nccl.GroupStart());
+                for (int d = 0; d < nranks; ++d) {
+                    NK(g_nccl.Send(l.send + (size_t)d * l.chunk, l.chunk * 2, /*ncclFloat*/ 7, d, comm, stream));
+                    NK(g_nccl.Recv(l.recv + (size_t)d * l.chunk, l.chunk * 2, 7, d, comm, stream));
+                }
+                NK(g_nccl.GroupEnd());
+                break;
+            }
+        }
+        return CUPSS_B200_OK;
+    }
+    int run_list(std::vector<Launch>& v) {
+        for (auto& l : v) CKR(run_launch(l));
+        return CUPSS_B200_OK;
+    }
+
+    // ------------------------------------------------------------ full transforms (upload / download; not on the hot path)
+    // real [zl][sy][sx] (realBuf) -> spectrum S
+    int forward_full(float2* S) {
+        std::vector<Launch> v;
+        float2 *t0, *t1;
+        CKR(get_scratch(0, &t0));
+        CKR(get_scratch(1, &t1));
+        Launch x{};
+        x.kind = Launch::XPASS; x.mode = X_R2C_ONLY;
+        x.xa.nIn = 0; x.xa.nOut = 1; x.xa.nMono = 0;
+        x.xa.out[0] = dim == 1 ? S : t0;
+        x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy; x.xa.norm = 1.0f; x.xa.realIn = realBuf;
+        CKR(get_twiddle(sx, &x.xa.tw));
+        v.push_back(x);
+        if (dim == 3) {
+            Launch y{};
+            y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = -1;
+            CKR(make_y_axis(y.ax, true));
+            y.ax.in = t0; y.ax.out = t1;
+            v.push_back(y);
+            const float2* zin = t1;
+            if (nranks > 1) { CKR(add_a2a(v, "a2a", t1, t0)); zin = t0; }
+            Launch z{};
+            z.kind = Launch::AXIS_PLAIN; z.dir = -1;
+            CKR(make_last_axis(z.ax, &z.L));
+            z.ax.in = zin; z.ax.out = S;
+            v.push_back(z);
+        } else if (dim == 2) {
+            Launch y{};
+            y.kind = Launch::AXIS_PLAIN; y.dir = -1;
+            CKR(make_last_axis(y.ax, &y.L));
+            y.ax.in = t0; y.ax.out = S;
+            v.push_back(y);
+        }
+        return run_list(v);
+    }
+    // spectrum S -> real (realBuf), normalised
+    int inverse_full(const float2* S) {
+        std::vector<Launch> v;
+        float2 *t0, *t1;
+        CKR(get_scratch(0, &t0));
+        CKR(get_scratch(1, &t1));
+        const float2* xin = S;
+        if (dim == 3) {
+            Launch z{};
+            z.kind = Launch::AXIS_PLAIN; z.dir = +1;
+            CKR(make_last_axis(z.ax, &z.L));
+            z.ax.in = S; z.ax.out = t0;
+            v.push_back(z);
+            const float2* yin = t0;
+            if (nranks > 1) { CKR(add_a2a(v, "a2a", t0, t1)); yin = t1; }
+            Launch y{};
+            y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = +1;
+            CKR(make_y_axis(y.ax, false));
+            float2* yo = yin == t0 ? t1 : t0;
+            y.ax.in = yin; y.ax.out = yo;
+            v.push_back(y);
+            xin = yo;
+        } else if (dim == 2) {
+            Launch y{};
+            y.kind = Launch::AXIS_PLAIN; y.dir = +1;
+            CKR(make_last_axis(y.ax, &y.L));
+            y.ax.in = S; y.ax.out = t0;
+            v.push_back(y);
+            xin = t0;
+        }
+        Launch x{};
+        x.kind = Launch::XPASS; x.mode = X_C2R_ONLY;
+        x.xa.nIn = 1; x.xa.nOut = 0; x.xa.nMono = 0;
+        x.xa.in[0] = xin;
+        x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
+        x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
+        x.xa.realOut = realBuf;
+        CKR(get_twiddle(sx, &x.xa.tw));
+        v.push_back(x);
+        return run_list(v);
+    }
+
+    // ------------------------------------------------------------ schedule construction
+    struct Mono { float coef; std::vector<int> fac; };
+    struct Group { int field; int firstTerm; std::vector<Pres> pres; std::vector<Mono> monos; };
+
+    static bool proportional(const std::vector<Pres>& a, const std::vector<Pres>& b, float* lambda) {
+        if (a.size() != b.size()) return false;
+        float lam = 0.0f; bool have = false;
+        for (size_t i = 0; i < a.size(); ++i) {
+            if (a[i].q2n != b[i].q2n || a[i].iqx != b[i].iqx || a[i].iqy != b[i].iqy || a[i].iqz != b[i].iqz || a[i].invq != b[i].invq) return false;
+            if (a[i].pre == 0.0f) { if (b[i].pre != 0.0f) return false; continue; }
+            const float l = b[i].pre / a[i].pre;
+            if (have && l != lam) return false;
+            lam = l; have = true;
+        }
+        if (!have) return false;
+        *lambda = lam;
+        return true;
+    }
+
+    static void fold_pres(const std::vector<Pres>& in, KStageD& ks, int& npresUsed, TermD& td) {
+        const int mulI = in.empty() ? 0 : ((in[0].iqx + in[0].iqy + in[0].iqz) % 2);
+        td.presOff = (short)npresUsed; td.npres = (signed char)in.size(); td.mulI = (signed char)mulI;
+        for (const Pres& p : in) {
+            const int units = p.iqx + p.iqy + p.iqz;
+            const int negate = -2 * (((units - mulI) / 2) % 2) + 1;   // term::precomputePrefactors, src/term_init.cpp:155
+            PresD d{};
+            d.pre = p.pre * (float)negate;
+            d.q2n = (signed char)p.q2n; d.iqx = (signed char)p.iqx; d.iqy = (signed char)p.iqy;
+            d.iqz = (signed char)p.iqz; d.invq = (signed char)p.invq;
+            ks.pres[npresUsed++] = d;
+        }
+    }
+
+    void cutoffs(int order, short* cx, short* cy, short* cz) const {
+        if (dealiasRule == CUPSS_B200_DEALIAS_GPU_RULE) {
+            *cx = (short)(sx / (order + 1)); *cy = (short)(sy / (order + 1)); *cz = (short)(sz / (order + 1));
+        } else {   // field::dealias CPU loop: third test repeats nj against sz (src/field.cpp:220)
+            const int a = sy / (order + 1), b = sz / (order + 1);
+            *cx = (short)(sx / (order + 1)); *cy = (short)(a < b ? a : b); *cz = 32767;
+        }
+    }
+
+    int build_stage(bool dyn, std::vector<Launch>& out) {
+        std::vector<int> outs;
+        for (size_t f = 0; f < fields.size(); ++f) if (fields[f].dynamic == dyn) outs.push_back((int)f);
+        if (outs.empty()) return CUPSS_B200_OK;
+        const char* tag = dyn ? "dyn" : "con";
+
+        // ---- product-term groups (terms of one field whose prefactor vectors are proportional share one forward transform)
+        std::vector<Group> groups;
+        for (int f : outs) {
+            for (size_t ti = 0; ti < fields[f].terms.size(); ++ti) {
+                const Term& t = fields[f].terms[ti];
+                if (t.product.size() == 1) continue;
+                bool allZero = true;
+                for (const Pres& p : t.pres) if (p.pre != 0.0f) allZero = false;
+                if (allZero) continue;   // RHS "0": contributes nothing
+                if (t.product.size() > (size_t)XP_MAX_FAC) return fail(CUPSS_B200_ERR_ARG, "product of %zu fields exceeds %d", t.product.size(), XP_MAX_FAC);
+                bool placed = false;
+                for (Group& g : groups) {
+                    float lam;
+                    if (g.field == f && proportional(g.pres, t.pres, &lam)) { g.monos.push_back({lam, t.product}); placed = true; break; }
+                }
+                if (!placed) groups.push_back({f, (int)ti, t.pres, {{1.0f, t.product}}});
+            }
+        }
+
+        size_t sc = 2;   // scratch 0,1 are reserved for upload/download
+        std::vector<const float2*> groupSpec(groups.size(), nullptr);   // input of the last-axis forward pass per group
+
+        // ---- x passes (greedy split under the kernel's descriptor limits)
+        size_t g0 = 0;
+        while (g0 < groups.size()) {
+            Launch x{};
+            x.kind = Launch::XPASS; x.mode = X_HOT;
+            snprintf(x.name, sizeof x.name, "x_%s", tag);
+            std::vector<int> ins;
+            size_t g1 = g0;
+            int nMono = 0;
+            while (g1 < groups.size()) {
+                std::vector<int> trial = ins;
+                int monos = nMono;
+                for (const Mono& m : groups[g1].monos) {
+                    ++monos;
+                    for (int fid : m.fac) {
+                        bool seen = false;
+                        for (int q : trial) if (q == fid) seen = true;
+                        if (!seen) trial.push_back(fid);
+                    }
+                }
+                if (g1 > g0 && (trial.size() > (size_t)XP_MAX_IN || monos > XP_MAX_MONO || g1 - g0 >= (size_t)XP_MAX_OUT)) break;
+                if (trial.size() > (size_t)XP_MAX_IN || monos > XP_MAX_MONO) return fail(CUPSS_B200_ERR_ARG, "a single term group needs too many fields/monomials");
+                ins = trial; nMono = monos; ++g1;
+            }
+            x.xa.nIn = (int)ins.size();
+            if (ins.empty()) {   // pure constants: still need one (dummy) input line; use the field's own W2
+                ins.push_back(groups[g0].field);
+                x.xa.nIn = 1;
+                Field& F0 = fields[groups[g0].field];
+                if (!F0.W2) {
+                    CK(cudaMalloc(&F0.W2, specElems * sizeof(float2)));
+                    CK(cudaMemsetAsync(F0.W2, 0, specElems * sizeof(float2), stream));
+                }
+            }
+            for (size_t i = 0; i < ins.size(); ++i) {
+                Field& F = fields[ins[i]];
+                if (!F.W2) return fail(CUPSS_B200_ERR_STATE, "internal: field %s has no dealiased buffer", F.name.c_str());
+                x.xa.in[i] = F.W2;
+            }
+            x.xa.nOut = (int)(g1 - g0);
+            int mi = 0;
+            for (size_t g = g0; g < g1; ++g) {
+                float2* w3;
+                CKR(get_scratch(sc++, &w3));
+                x.xa.out[g - g0] = w3;
+                groupSpec[g] = w3;
+                for (const Mono& m : groups[g].monos) {
+                    XMono xm{};
+                    xm.coef = m.coef; xm.out = (signed char)(g - g0); xm.nfac = (signed char)m.fac.size();
+                    for (size_t q = 0; q < m.fac.size(); ++q)
+                        for (size_t i = 0; i < ins.size(); ++i) if (ins[i] == m.fac[q]) xm.fac[q] = (signed char)i;
+                    x.xa.mono[mi++] = xm;
+                }
+            }
+            x.xa.nMono = mi;
+            x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
+            x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
+            CKR(get_twiddle(sx, &x.xa.tw));
+            x.bytes = (double)(x.xa.nIn + x.xa.nOut) * spec_bytes();
+            out.push_back(x);
+            g0 = g1;
+        }
+
+        // ---- forward y passes (3-D) and slab exchange
+        if (dim == 3) {
+            for (size_t g = 0; g < groups.size(); ++g) {
+                Launch y{};
+                y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = -1;
+                snprintf(y.name, sizeof y.name, "yfwd_%s", tag);
+                CKR(make_y_axis(y.ax, true));
+                float2* w4;
+                CKR(get_scratch(sc++, &w4));
+                y.ax.in = groupSpec[g]; y.ax.out = w4;
+                y.bytes = 2.0 * spec_bytes();
+                out.push_back(y);
+                groupSpec[g] = w4;
+                if (nranks > 1) {
+                    float2* r;
+                    CKR(get_scratch(sc++, &r));
+                    CKR(add_a2a(out, "a2a_fwd", w4, r));
+                    groupSpec[g] = r;
+                }
+            }
+        }
+
+        // ---- k stage
+        Launch k{};
+        k.kind = Launch::AXIS_KSTAGE;
+        snprintf(k.name, sizeof k.name, "kstage_%s", tag);
+        CKR(make_last_axis(k.ax, &k.L));
+        KStageD& ks = k.ks;
+        ks.dt = dt; ks.sdt = 1.0f / std::sqrt(dt); ks.noiseBase = dt / (dx * dy * dz);
+        ks.stepqx = 2.0f * 3.1415926535f / (dx * (float)sx);   // PI as in inc/cupss/defines.h:54
+        ks.stepqy = 2.0f * 3.1415926535f / (dy * (float)sy);
+        ks.stepqz = 2.0f * 3.1415926535f / (dz * (float)sz);
+        ks.sx = sx; ks.sy = sy; ks.sz = sz;
+        ks.stepCounter = stepCounter;
+        ks.seed = 0;
+        ks.hasFwd = groups.empty() ? 0 : 1;
+        if (ks.hasFwd) k.ax.in = groupSpec[0];
+
+        std::map<int, int> srcOfField;
+        auto srcField = [&](int f) -> int {
+            auto it = srcOfField.find(f);
+            if (it != srcOfField.end()) return it->second;
+            if (ks.nsrc >= KS_MAX_SRC) return -100;
+            ks.src[ks.nsrc] = fields[f].S;
+            srcOfField[f] = ks.nsrc;
+            return ks.nsrc++;
+        };
+        // groups beyond the first get their own last-axis forward pass into a spectrum that the k stage reads pointwise
+        std::vector<int> srcOfGroup(groups.size(), -1);
+        for (size_t g = 1; g < groups.size(); ++g) {
+            Launch z{};
+            z.kind = Launch::AXIS_PLAIN; z.dir = -1;
+            snprintf(z.name, sizeof z.name, "lastfwd_%s", tag);
+            CKR(make_last_axis(z.ax, &z.L));
+            float2* that;
+            CKR(get_scratch(sc++, &that));
+            z.ax.in = groupSpec[g]; z.ax.out = that;
+            z.bytes = 2.0 * spec_bytes();
+            out.push_back(z);
+            if (ks.nsrc >= KS_MAX_SRC) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
+            ks.src[ks.nsrc] = that;
+            srcOfGroup[g] = ks.nsrc++;
+        }
+
+        int nterm = 0, npres = 0;
+        int invField = -1;
+        std::vector<int> extraInv;
+        for (int f : outs) {
+            Field& F = fields[f];
+            if (ks.nout >= KS_MAX_OUT) return fail(CUPSS_B200_ERR_ARG, "more than %d fields in one sweep", KS_MAX_OUT);
+            OutD& od = ks.out[ks.nout];
+            od = OutD{};
+            od.dynamic = F.dynamic; od.fieldId = (signed char)f;
+            const int self = srcField(f);
+            if (self < 0) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
+            od.selfSrc = (signed char)self;
+            od.dst = (signed char)ks.nout;
+            ks.dst[ks.nout] = F.S;
+            od.termOff = (short)nterm;
+            for (size_t ti = 0; ti < F.terms.size(); ++ti) {
+                const Term& t = F.terms[ti];
+                int src = -100;
+                const std::vector<Pres>* pv = &t.pres;
+                if (t.product.size() == 1) {
+                    src = srcField(t.product[0]);
+                    if (src < 0) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
+                } else {
+                    bool found = false;
+                    for (size_t g = 0; g < groups.size(); ++g)
+                        if (groups[g].field == f && groups[g].firstTerm == (int)ti) { src = g == 0 ? -1 : srcOfGroup[g]; pv = &groups[g].pres; found = true; }
+                    if (!found) continue;   // merged into an earlier group, or identically zero
+                }
+                if (nterm >= KS_MAX_TERM || npres + (int)pv->size() > KS_MAX_PRES) return fail(CUPSS_B200_ERR_ARG, "too many terms/prefactors in one sweep");
+                TermD td{};
+                fold_pres(*pv, ks, npres, td);
+                td.src = (signed char)src;
+                ks.term[nterm++] = td;
+                od.nterm++;
+            }
+            od.impOff = (short)npres; od.nimp = (signed char)F.implicit.size();
+            if (npres + (int)F.implicit.size() > KS_MAX_PRES) return fail(CUPSS_B200_ERR_ARG, "too many prefactors in one sweep");
+            for (const Pres& p : F.implicit) {
+                PresD d{};
+                d.pre = p.pre; d.q2n = (signed char)p.q2n; d.invq = (signed char)p.invq;
+                ks.pres[npres++] = d;
+            }
+            od.noisy = F.noisy;
+            if (F.noisy) {
+                od.noise.pre = F.noise.pre; od.noise.q2n = (signed char)F.noise.q2n; od.noise.invq = (signed char)F.noise.invq;
+                ks.seed = F.seed;
+            }
+            cutoffs(F.aliasOrder, &od.cutx, &od.cuty, &od.cutz);
+            if (F.needsAlias) {
+                if (invField < 0) { invField = f; od.inv = 1; } else extraInv.push_back(f);
+            }
+            ks.nout++;
+        }
+        ks.hasInv = invField >= 0 ? 1 : 0;
+        float2* invOut = nullptr;
+        if (ks.hasInv) {
+            if (dim == 3) CKR(get_scratch(sc++, &invOut)); else invOut = fields[invField].W2;
+        }
+        k.ax.out = invOut ? invOut : fields[outs[0]].S;   // only its addressing is used when there is no fused inverse
+        k.bytes = (double)(ks.hasFwd + ks.nsrc + ks.nout + ks.hasInv) * spec_bytes();
+        out.push_back(k);
+
+        // ---- remaining inverse transforms of dealiased fields
+        std::vector<std::pair<int, float2*>> w1s;
+        if (invField >= 0 && dim == 3) w1s.push_back({invField, invOut});
+        for (int f : extraInv) {
+            Launch z{};
+            z.kind = Launch::AXIS_PLAIN; z.dir = +1;
+            snprintf(z.name, sizeof z.name, "lastinv_%s", tag);
+            CKR(make_last_axis(z.ax, &z.L));
+            z.ax.maskOn = 1;
+            short cx, cy, cz;
+            cutoffs(fields[f].aliasOrder, &cx, &cy, &cz);
+            z.ax.cutx = cx; z.ax.cuty = cy; z.ax.cutz = cz;
+            z.ax.in = fields[f].S;
+            float2* w1 = fields[f].W2;
+            if (dim == 3) CKR(get_scratch(sc++, &w1));
+            z.ax.out = w1;
+            z.bytes = 2.0 * spec_bytes();
+            out.push_back(z);
+            if (dim == 3) w1s.push_back({f, w1});
+        }
+        for (auto& pr : w1s) {
+            const float2* yin = pr.second;
+            if (nranks > 1) {
+                float2* r;
+                CKR(get_scratch(sc++, &r));
+                CKR(add_a2a(out, "a2a_inv", pr.second, r));
+                yin = r;
+            }
+            Launch y{};
+            y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = +1;
+            snprintf(y.name, sizeof y.name, "yinv_%s", tag);
+            CKR(make_y_axis(y.ax, false));
+            y.ax.in = yin; y.ax.out = fields[pr.first].W2;
+            y.bytes = 2.0 * spec_bytes();
+            out.push_back(y);
+        }
+        return CUPSS_B200_OK;
+    }
+
+    int drop_graph() {
+        if (graphExec) { cudaGraphExecDestroy(graphExec); graphExec = nullptr; }
+        return CUPSS_B200_OK;
+    }
+
+    int finalize() {
+        if (nranks > 1 && dim != 3) return fail(CUPSS_B200_ERR_ARG, "slab partitioning needs a 3-D grid");
+        drop_graph();
+        // aliasing flags (term::prepareDevice, src/term_init.cpp:118-126)
+        for (Field& F : fields) { F.needsAlias = false; F.aliasOrder = 1; }
+        for (Field& F : fields)
+            for (Term& t : F.terms)
+                if (t.product.size() != 1)
+                    for (int g : t.product) {
+                        fields[g].needsAlias = true;
+                        if (fields[g].aliasOrder < (int)t.product.size()) fields[g].aliasOrder = (int)t.product.size();
+                    }
+        for (Field& F : fields) {
+            if (!F.S) {
+                CK(cudaMalloc(&F.S, specElems * sizeof(float2)));
+                CK(cudaMemsetAsync(F.S, 0, specElems * sizeof(float2), stream));
+            }
+            if (F.needsAlias && !F.W2) {
+                CK(cudaMalloc(&F.W2, specElems * sizeof(float2)));
+                CK(cudaMemsetAsync(F.W2, 0, specElems * sizeof(float2), stream));   // real_dealiased starts at zero
+            }
+        }
+        step.clear();
+        CKR(build_stage(false, step));
+        CKR(build_stage(true, step));
+        Launch b{};
+        b.kind = Launch::BUMP;
+        snprintf(b.name, sizeof b.name, "bump");
+        step.push_back(b);
+        CK(cudaStreamSynchronize(stream));
+        finalized = true;
+        return CUPSS_B200_OK;
+    }
+
+    int capture_graph() {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int r = run_list(step);
+        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        if (r != CUPSS_B200_OK) { if (g) cudaGraphDestroy(g); return r; }
+        CK(e);
+        CK(cudaGraphInstantiate(&graphExec, g, 0));
+        CK(cudaGraphDestroy(g));
+        return CUPSS_B200_OK;
+    }
+
+    int do_steps(int n) {
+        if (!finalized) return fail(CUPSS_B200_ERR_STATE, "step before finalize");
+        if (useGraph && !graphExec) {
+            // run one step eagerly first so every kernel's attributes are set outside the capture
+            CKR(run_list(step));
+            --n;
+            CKR(capture_graph());
+        }
+        for (int i = 0; i < n; ++i) {
+            if (useGraph) CK(cudaGraphLaunch(graphExec, stream));
+            else CKR(run_list(step));
+        }
+        return CUPSS_B200_OK;
+    }
+};
+
+// ---------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* cupss_b200_last_error(void) { return g_err; }
+
+int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, float dy, float dz, float dt) {
+    if (!out) return fail(CUPSS_B200_ERR_ARG, "null out pointer");
+    if (sx < 2 || sy < 1 || sz < 1) return fail(CUPSS_B200_ERR_ARG, "bad grid %dx%dx%d", sx, sy, sz);
+    if (!fft_size_supported(sx) || !fft_size_supported(sy) || !fft_size_supported(sz) || sx > 8192)
+        return fail(CUPSS_B200_ERR_ARG, "grid %dx%dx%d: every axis must be a power of two <= 8192", sx, sy, sz);
+    if (sy == 1 && sz > 1) return fail(CUPSS_B200_ERR_ARG, "sy == 1 with sz > 1 is not a valid cuPSS grid");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CUPSS_B200_ERR_CUDA, "no CUDA device available (%s): the B200 engine has no CPU fallback", cudaGetErrorString(e));
+    cupss_b200_plan* p = new cupss_b200_plan();
+    p->sx = sx; p->sy = sy; p->sz = sz; p->dx = dx; p->dy = dy; p->dz = dz; p->dt = dt;
+    p->dim = sz > 1 ? 3 : (sy > 1 ? 2 : 1);
+    p->zl = sz; p->kyl = sy;
+    p->ncol = sx / 2 + 1;
+    p->pitch = (p->ncol + 15) / 16 * 16;
+    p->specElems = (size_t)p->pitch * sy * sz;
+    const char* ng = getenv("CUPSS_B200_NO_GRAPH");
+    p->useGraph = !(ng && ng[0] == '1');
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&p->ev0));
+    CK(cudaEventCreate(&p->ev1));
+    CK(cudaMalloc(&p->stepCounter, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(p->stepCounter, 0, sizeof(unsigned int), p->stream));
+    *out = p;
+    return CUPSS_B200_OK;
+}
+
+void cupss_b200_destroy(cupss_b200_plan* p) {
+    if (!p) return;
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    p->drop_graph();
+    for (Field& F : p->fields) { if (F.S) cudaFree(F.S); if (F.W2) cudaFree(F.W2); }
+    for (float2* s : p->scratch) if (s) cudaFree(s);
+    for (auto& kv : p->twiddles) cudaFree(kv.second);
+    if (p->realBuf) cudaFree(p->realBuf);
+    if (p->stepCounter) cudaFree(p->stepCounter);
+    if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int cupss_b200_nccl_unique_id(void* id128) {
+    CKR(load_nccl());
+    NK(g_nccl.GetUniqueId(id128));
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_set_partition(cupss_b200_plan* p, int rank, int nranks, const void* id) {
+    if (!p || nranks < 1 || rank < 0 || rank >= nranks) return fail(CUPSS_B200_ERR_ARG, "bad rank %d/%d", rank, nranks);
+    if (!p->fields.empty() && p->fields[0].S) return fail(CUPSS_B200_ERR_STATE, "set_partition must precede finalize/upload");
+    if (nranks == 1) return CUPSS_B200_OK;
+    if (p->dim != 3) return fail(CUPSS_B200_ERR_ARG, "slab partitioning needs a 3-D grid");
+    if (p->sz % nranks || p->sy % nranks || (nranks & (nranks - 1))) return fail(CUPSS_B200_ERR_ARG, "sz and sy must be divisible by a power-of-two rank count");
+    CKR(load_nccl());
+    Id128 uid;
+    memcpy(uid.b, id, 128);
+    NK(g_nccl.CommInitRank(&p->comm, nranks, uid, rank));
+    p->rank = rank; p->nranks = nranks;
+    p->zl = p->sz / nranks; p->kyl = p->sy / nranks;
+    p->specElems = (size_t)p->pitch * p->kyl * p->sz;   // == pitch * sy * zl
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_add_field(cupss_b200_plan* p, const char* name, int dynamic) {
+    if (!p || !name) { fail(CUPSS_B200_ERR_ARG, "null argument"); return -CUPSS_B200_ERR_ARG; }
+    Field F;
+    F.name = name; F.dynamic = dynamic != 0;
+    p->fields.push_back(F);
+    p->finalized = false;
+    return (int)p->fields.size() - 1;
+}
+
+static int check_field(cupss_b200_plan* p, int f) {
+    if (!p || f < 0 || f >= (int)p->fields.size()) return fail(CUPSS_B200_ERR_ARG, "bad field id %d", f);
+    return CUPSS_B200_OK;
+}
+static Pres to_pres(const cupss_b200_pres& q) { return Pres{q.preFactor, q.q2n, q.iqx, q.iqy, q.iqz, q.invq}; }
+
+int cupss_b200_set_implicit(cupss_b200_plan* p, int f, const cupss_b200_pres* pres, int n) {
+    CKR(check_field(p, f));
+    p->fields[f].implicit.clear();
+    for (int i = 0; i < n; ++i) p->fields[f].implicit.push_back(to_pres(pres[i]));
+    p->finalized = false;
+    return CUPSS_B200_OK;
+}
+int cupss_b200_clear_terms(cupss_b200_plan* p, int f) {
+    CKR(check_field(p, f));
+    p->fields[f].terms.clear();
+    p->finalized = false;
+    return CUPSS_B200_OK;
+}
+int cupss_b200_add_term(cupss_b200_plan* p, int f, const cupss_b200_pres* pres, int n, const int* product, int m) {
+    CKR(check_field(p, f));
+    if (n < 1) return fail(CUPSS_B200_ERR_ARG, "a term needs at least one prefactor");
+    Term t;
+    for (int i = 0; i < n; ++i) t.pres.push_back(to_pres(pres[i]));
+    for (int i = 0; i < m; ++i) {
+        CKR(check_field(p, product[i]));
+        t.product.push_back(product[i]);
+    }
+    p->fields[f].terms.push_back(t);
+    p->finalized = false;
+    return CUPSS_B200_OK;
+}
+int cupss_b200_set_noise(cupss_b200_plan* p, int f, const cupss_b200_pres* amp, unsigned long long seed) {
+    CKR(check_field(p, f));
+    p->fields[f].noisy = amp != nullptr;
+    if (amp) p->fields[f].noise = to_pres(*amp);
+    p->fields[f].seed = seed;
+    p->finalized = false;
+    return CUPSS_B200_OK;
+}
+int cupss_b200_set_dealias_rule(cupss_b200_plan* p, int rule) {
+    if (!p || (rule != CUPSS_B200_DEALIAS_GPU_RULE && rule != CUPSS_B200_DEALIAS_CPU_RULE)) return fail(CUPSS_B200_ERR_ARG, "bad dealias rule");
+    p->dealiasRule = rule;
+    p->finalized = false;
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_finalize(cupss_b200_plan* p) {
+    if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
+    return p->finalize();
+}
+
+static int ensure_real_buf(cupss_b200_plan* p) {
+    if (!p->realBuf) CK(cudaMalloc(&p->realBuf, (size_t)p->sx * p->sy * p->zl * sizeof(float)));
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_upload_real(cupss_b200_plan* p, int f, const float* host) {
+    CKR(check_field(p, f));
+    if (!host) return fail(CUPSS_B200_ERR_ARG, "null host pointer");
+    Field& F = p->fields[f];
+    if (!F.S) {
+        CK(cudaMalloc(&F.S, p->specElems * sizeof(float2)));
+        CK(cudaMemsetAsync(F.S, 0, p->specElems * sizeof(float2), p->stream));
+    }
+    CKR(ensure_real_buf(p));
+    const size_t n = (size_t)p->sx * p->sy * p->zl;
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = host[2 * i];   // value lives in .x (inc/cupss/field.h:67)
+    CK(cudaMemcpyAsync(p->realBuf, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CKR(p->forward_full(F.S));
+    CK(cudaStreamSynchronize(p->stream));
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_download_real(cupss_b200_plan* p, int f, float* host) {
+    CKR(check_field(p, f));
+    Field& F = p->fields[f];
+    if (!F.S || !host) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
+    CKR(ensure_real_buf(p));
+    CKR(p->inverse_full(F.S));
+    const size_t n = (size_t)p->sx * p->sy * p->zl;
+    std::vector<float> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), p->realBuf, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (size_t i = 0; i < n; ++i) { host[2 * i] = tmp[i]; host[2 * i + 1] = 0.0f; }
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_download_comp(cupss_b200_plan* p, int f, float* host) {
+    CKR(check_field(p, f));
+    Field& F = p->fields[f];
+    if (!F.S || !host) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
+    if (p->nranks != 1) return fail(CUPSS_B200_ERR_ARG, "download_comp is single-rank only");
+    std::vector<float2> half(p->specElems);
+    CK(cudaMemcpyAsync(half.data(), F.S, p->specElems * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const int sx = p->sx, sy = p->sy, sz = p->sz, pitch = p->pitch;
+    for (int k = 0; k < sz; ++k)
+        for (int j = 0; j < sy; ++j)
+            for (int i = 0; i < sx; ++i) {
+                float2 v;
+                if (i <= sx / 2) v = half[((size_t)k * sy + j) * pitch + i];
+                else {
+                    const int mk = (sz - k) % sz, mj = (sy - j) % sy;
+                    v = half[((size_t)mk * sy + mj) * pitch + (sx - i)];
+                    v.y = -v.y;
+                }
+                const size_t o = ((size_t)k * sy + j) * sx + i;
+                host[2 * o] = v.x; host[2 * o + 1] = v.y;
+            }
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_step(cupss_b200_plan* p, int nsteps) {
+    if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
+    return p->do_steps(nsteps);
+}
+int cupss_b200_sync(cupss_b200_plan* p) {
+    if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
+    CK(cudaStreamSynchronize(p->stream));
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_field_alias(cupss_b200_plan* p, int f, int* needs, int* order) {
+    CKR(check_field(p, f));
+    if (needs) *needs = p->fields[f].needsAlias;
+    if (order) *order = p->fields[f].aliasOrder;
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_time_steps(cupss_b200_plan* p, int nsteps, float* ms) {
+    if (!p || !ms) return fail(CUPSS_B200_ERR_ARG, "null argument");
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaEventRecord(p->ev0, p->stream));
+    CKR(p->do_steps(nsteps));
+    CK(cudaEventRecord(p->ev1, p->stream));
+    CK(cudaEventSynchronize(p->ev1));
+    CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_profile_step(cupss_b200_plan* p, int nmax, char* names, float* ms, double* bytes, int* n) {
+    if (!p || !p->finalized) return fail(CUPSS_B200_ERR_STATE, "profile before finalize");
+    const int cnt = (int)p->step.size();
+    std::vector<cudaEvent_t> ev(cnt + 1);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaEventRecord(ev[0], p->stream));
+    for (int i = 0; i < cnt; ++i) {
+        CKR(p->run_launch(p->step[i]));
+        CK(cudaEventRecord(ev[i + 1], p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    for (int i = 0; i < cnt && i < nmax; ++i) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        if (ms) ms[i] = t;
+        if (bytes) bytes[i] = p->step[i].bytes;
+        if (names) snprintf(names + 64 * i, 64, "%s", p->step[i].name);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (n) *n = cnt < nmax ? cnt : nmax;
+    return CUPSS_B200_OK;
+}
+
+int cupss_b200_launches_per_step(cupss_b200_plan* p) {
+    if (!p) return 0;
+    int c = 0;
+    for (auto& l : p->step) if (l.kind != Launch::A2A) ++c;
+    return c;
+}
+double cupss_b200_bytes_per_step(cupss_b200_plan* p) {
+    double b = 0;
+    if (p) for (auto& l : p->step) if (l.kind != Launch::A2A) b += l.bytes;
+    return b;
+}
+double cupss_b200_comm_bytes_per_step(cupss_b200_plan* p) {
+    double b = 0;
+    if (p) for (auto& l : p->step) if (l.kind == Launch::A2A) b += l.bytes;
+    return b;
+}
+void* cupss_b200_device_spectrum(cupss_b200_plan* p, int f) {
+    if (!p || f < 0 || f >= (int)p->fields.size()) return nullptr;
+    return p->fields[f].S;
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// kernels.h -- host-visible launch interface of the sm_100a step kernels (internal to the engine).
+#pragma once
+#include <cuda_runtime.h>
+#include "kstage.cuh"
+
+namespace cupss {
+
+// Addressing of one side (input or output) of a strided-axis pass.  Row r of batch b, column c:
+//   b*bs + (r >> rpcShift)*cs + (r & (rpc-1))*rs + c          (float2 elements)
+// Natural layouts use rpc = L (one chunk).  The multi-GPU exchange layout [peer][z_loc][ky_loc][kx]
+// of the y pass uses rpc = ky_loc count, cs = peer chunk stride.
+struct AxisAddr {
+    long long bs, cs, rs;
+    int rpcShift, rpcMask;
+};
+
+struct AxisArgs {
+    const float2* in;
+    float2* out;
+    AxisAddr ain, aout;
+    int ncol;        // valid columns (sx/2 + 1)
+    int ncolTiles;   // ceil(ncol / C)
+    int nbatch;
+    const float2* tw;
+    int axis;        // k index carried by the rows: 1 = ky, 2 = kz, 0 = none (L = 1)
+    int kyBase;      // axis == 2: iky = kyBase + batch
+    int maskOn, cutx, cuty, cutz;   // plain inverse: dealias mask applied on load
+    int sx, sy, sz;
+};
+
+// x pass: C2R of up to XP_MAX_IN half-spectrum lines, real-space products, R2C of the results
+// (computeProduct_k + normalize_k + the x part of every cuFFT call; /root/reference/src/term_kernels.cu:48-70,
+//  src/field_kernels.cu:115-128).
+constexpr int XP_MAX_IN = 8;
+constexpr int XP_MAX_OUT = 6;
+constexpr int XP_MAX_MONO = 16;
+constexpr int XP_MAX_FAC = 6;
+struct XMono {
+    float coef;
+    signed char out, nfac;
+    signed char fac[XP_MAX_FAC];
+};
+struct XArgs {
+    const float2* in[XP_MAX_IN];
+    float2* out[XP_MAX_OUT];
+    XMono mono[XP_MAX_MONO];
+    int nIn, nOut, nMono;
+    int pitch;
+    long long nlines;
+    float norm;      // 1 / (sx*sy*sz)
+    const float2* tw;
+    float* realOut;        // mode C2R_ONLY: [nlines][sx]
+    const float* realIn;   // mode R2C_ONLY
+    int jobsPerCta;
+    int perJobFloat2;      // shared-memory float2 per job
+};
+
+enum XMode { X_HOT = 0, X_C2R_ONLY = 1, X_R2C_ONLY = 2 };
+
+// Launchers return cudaError_t of the launch; unsupported sizes return cudaErrorInvalidValue.
+cudaError_t launch_axis_plain(int L, int dir, const AxisArgs& a, cudaStream_t st);
+cudaError_t launch_axis_kstage(int L, const AxisArgs& a, const KStageD& ks, cudaStream_t st);
+cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st);
+cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
+int axis_tile_cols(int L);          // C used for length L
+bool fft_size_supported(int n);
+
+}  // namespace cupss

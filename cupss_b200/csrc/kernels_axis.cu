@@ -1,0 +1,191 @@
+// kernels_axis.cu -- strided-axis FFT passes (y and z) of the half-spectrum, plain and fused.
+//
+// A CTA owns a tile [L rows] x [C columns] of one k-space array: the L points of C neighbouring
+// kx columns along the transformed axis.  Lanes map to columns, so every global access of a
+// half-warp is one contiguous, 128-byte-aligned row segment (C = 16 float2) and every
+// shared-memory access is conflict-free.  Thread (t, c) owns points t + T*e of column c.
+//
+//   axis_plain_kernel  : load -> FFT -> store                      (y passes of a 3-D transform;
+//                        optional dealias mask on load for extra inverse transforms)
+//   axis_kstage_kernel : [load -> forward FFT] -> per-mode update of every field of the sweep
+//                        (kstage_point) -> [dealias -> inverse FFT -> store]
+// The second is the heart of the step: the last pass of the forward transform of the nonlinear
+// term, the semi-implicit Euler update, the dealiasing mask and the first pass of the next inverse
+// transform happen on data that never leaves the SM.
+#include "kernels.h"
+
+namespace cupss {
+
+template <int C, int PADR>
+struct TileEx {
+    float2* buf;
+    int c;
+    __device__ __forceinline__ static int prow(int idx) { return PADR > 0 ? idx + idx / PADR : idx; }
+    __device__ __forceinline__ void st(int idx, float2 v) { buf[prow(idx) * C + c] = v; }
+    __device__ __forceinline__ float2 ld(int idx) const { return buf[prow(idx) * C + c]; }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+template <int L> struct AxisCfg {
+    static constexpr int C = L <= 512 ? 16 : (L <= 2048 ? 8 : (L <= 4096 ? 4 : 2));
+    static constexpr int PADR = C < 16 ? FftPlan<L>::R0 : 0;
+    static constexpr int ROWS = PADR > 0 ? L + L / PADR + 1 : L;
+    static constexpr int THREADS = FftPlan<L>::T * C;
+    static constexpr size_t SMEM = FftPlan<L>::R1 > 1 ? (size_t)ROWS * C * sizeof(float2) : 0;
+};
+
+__device__ __forceinline__ long long axis_off(const AxisAddr& a, int b, int row, int col) {
+    return (long long)b * a.bs + (long long)(row >> a.rpcShift) * a.cs + (long long)(row & a.rpcMask) * a.rs + col;
+}
+
+template <int L, int DIR>
+__global__ void __launch_bounds__(AxisCfg<L>::THREADS) axis_plain_kernel(const __grid_constant__ AxisArgs a) {
+    using P = FftPlan<L>;
+    constexpr int E = P::E, T = P::T, C = AxisCfg<L>::C;
+    extern __shared__ float2 smem[];
+    const int c = threadIdx.x % C, t = threadIdx.x / C;
+    const int ct = blockIdx.x % a.ncolTiles, b = blockIdx.x / a.ncolTiles;
+    const int col = ct * C + c;
+    const bool valid = col < a.ncol;
+    TileEx<C, AxisCfg<L>::PADR> ex{smem, c};
+
+    float2 v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int row = t + T * e;
+        bool keep = valid;
+        if (a.maskOn) {
+            const int iy = a.axis == 2 ? a.kyBase + b : (a.axis == 1 ? row : 0);
+            const int iz = a.axis == 2 ? row : 0;
+            keep = keep && dealias_keep(col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz);
+        }
+        v[e] = keep ? __ldg(a.in + axis_off(a.ain, b, row, col)) : make_float2(0.0f, 0.0f);
+    }
+    fft_line<L, DIR>(v, t, a.tw, ex);
+    if (valid) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(AxisCfg<L>::THREADS)
+axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
+    using P = FftPlan<L>;
+    constexpr int E = P::E, T = P::T, C = AxisCfg<L>::C;
+    extern __shared__ float2 smem[];
+    const int c = threadIdx.x % C, t = threadIdx.x / C;
+    const int ct = blockIdx.x % a.ncolTiles, b = blockIdx.x / a.ncolTiles;
+    const int col = ct * C + c;
+    const bool valid = col < a.ncol;
+    TileEx<C, AxisCfg<L>::PADR> ex{smem, c};
+
+    float2 v[E];
+    if (ks.hasFwd) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            v[e] = valid ? __ldg(a.in + axis_off(a.ain, b, t + T * e, col)) : make_float2(0.0f, 0.0f);
+        fft_line<L, -1>(v, t, a.tw, ex);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = make_float2(0.0f, 0.0f);
+    }
+
+    const unsigned int step = ks.stepCounter ? *ks.stepCounter : 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int row = t + T * e;
+        const int iy = a.axis == 2 ? a.kyBase + b : (a.axis == 1 ? row : 0);
+        const int iz = a.axis == 2 ? row : 0;
+        if (valid) {
+            const KPoint k = make_kpoint(ks, col, iy, iz);
+            // k-space arrays share the natural addressing of the pass output
+            v[e] = kstage_point(ks, k, v[e], axis_off(a.aout, b, row, col), step);
+        } else {
+            v[e] = make_float2(0.0f, 0.0f);
+        }
+    }
+
+    if (ks.hasInv) {
+        if (ks.hasFwd && P::R1 > 1) __syncthreads();   // exchange buffer still being read by the forward transform
+        fft_line<L, +1>(v, t, a.tw, ex);
+        if (valid) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+        }
+    }
+}
+
+__global__ void bump_counter_kernel(unsigned int* c) { *c += 1u; }
+
+// ---------------------------------------------------------------- dispatch
+template <int L>
+static cudaError_t launch_plain_L(int dir, const AxisArgs& a, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (AxisCfg<L>::SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(axis_plain_kernel<L, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(axis_plain_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        attr = true;
+    }
+    const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
+    if (dir < 0) axis_plain_kernel<L, -1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+    else axis_plain_kernel<L, 1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int L>
+static cudaError_t launch_kstage_L(const AxisArgs& a, const KStageD& ks, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (AxisCfg<L>::SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(axis_kstage_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        attr = true;
+    }
+    const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
+    axis_kstage_kernel<L><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+    return cudaGetLastError();
+}
+
+#define CUPSS_FOR_SIZES(X) X(1) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+
+cudaError_t launch_axis_plain(int L, int dir, const AxisArgs& a, cudaStream_t st) {
+    switch (L) {
+#define X(N) case N: return launch_plain_L<N>(dir, a, st);
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_axis_kstage(int L, const AxisArgs& a, const KStageD& ks, cudaStream_t st) {
+    switch (L) {
+#define X(N) case N: return launch_kstage_L<N>(a, ks, st);
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+int axis_tile_cols(int L) {
+    switch (L) {
+#define X(N) case N: return AxisCfg<N>::C;
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return 0;
+}
+
+bool fft_size_supported(int n) { return axis_tile_cols(n) != 0; }
+
+cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st) {
+    bump_counter_kernel<<<1, 1, 0, st>>>(counter);
+    return cudaGetLastError();
+}
+
+}  // namespace cupss

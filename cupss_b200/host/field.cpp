@@ -1,0 +1,96 @@
+// field.cpp -- host side of a field: mirrors, CSV output, parameter updates.
+// Device work of the reference's field.cpp/field_init.cpp (updateTerms, setRHS, toReal, toComp, dealias,
+// normalize, createNoise, precalculateImplicit) is fused inside the engine; see cupss_b200/csrc/kstage.cuh.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../inc/cupss.h"
+
+static float q_step(float d, int n) { return 2.0f * PI / (d * (float)n); }
+
+field::field(int nx, float hx)
+    : sx(nx), sy(1), sz(1), dx(hx), dy(1.0f), dz(1.0f), stepqx(q_step(hx, nx)), stepqy(2.0f * PI), stepqz(2.0f * PI) {
+    real_array = new float2[(size_t)sx * sy * sz]();
+    comp_array = new float2[(size_t)sx * sy * sz]();
+}
+field::field(int nx, int ny, float hx, float hy)
+    : sx(nx), sy(ny), sz(1), dx(hx), dy(hy), dz(1.0f), stepqx(q_step(hx, nx)), stepqy(q_step(hy, ny)), stepqz(2.0f * PI) {
+    real_array = new float2[(size_t)sx * sy * sz]();
+    comp_array = new float2[(size_t)sx * sy * sz]();
+}
+field::field(int nx, int ny, int nz, float hx, float hy, float hz)
+    : sx(nx), sy(ny), sz(nz), dx(hx), dy(hy), dz(hz), stepqx(q_step(hx, nx)), stepqy(q_step(hy, ny)), stepqz(q_step(hz, nz)) {
+    real_array = new float2[(size_t)sx * sy * sz]();
+    comp_array = new float2[(size_t)sx * sy * sz]();
+}
+
+field::~field() {
+    delete[] real_array;
+    delete[] comp_array;
+    for (term *t : terms) delete t;
+}
+
+float field::getStepqx() { return stepqx; }
+float field::getStepqy() { return stepqy; }
+float field::getStepqz() { return stepqz; }
+
+// The engine owns device state; these keep the reference's names for user code that calls them.
+void field::copyHostToDevice() { if (system_p) system_p->markPlanDirty(); }
+void field::copyRealHostToDevice() { if (system_p) system_p->markPlanDirty(); }
+void field::copyDeviceToHost() { if (system_p) system_p->refreshHostMirror(this, true, true); }
+void field::copyRealDeviceToHost() { if (system_p) system_p->refreshHostMirror(this, true, false); }
+void field::prepareDevice() { for (term *t : terms) t->prepareDevice(); }
+void field::precalculateImplicit(float) { /* implicit and noise factors are evaluated in-kernel from the mode index */ }
+
+// data/<name>.csv.<step>: header "x, [y, [z, ]]<name>", rows "%i, [%i, [%i, ]]%.<precision>f"
+// (format of /root/reference/src/field.cpp:350-402; NaN aborts with exit(1)).
+void field::writeToFile(int step, int dim, int precision) {
+    if (!outputToFile) return;
+    copyRealDeviceToHost();
+    const std::string path = "data/" + name + ".csv." + std::to_string(step);
+    FILE *fp = std::fopen(path.c_str(), "w+");
+    if (!fp) {
+        std::cout << "Error creating output file at timestep" << step << std::endl;
+        std::exit(1);
+    }
+    std::fprintf(fp, dim == 1 ? "x, %s\n" : (dim == 2 ? "x, y, %s\n" : "x, y, z, %s\n"), name.c_str());
+    const std::string vf = "%." + std::to_string(precision) + "f\n";
+    for (int k = 0; k < sz; k++)
+        for (int j = 0; j < sy; j++)
+            for (int i = 0; i < sx; i++) {
+                const float v = real_array[((size_t)k * sy + j) * sx + i].x;
+                if (std::isnan(v)) {
+                    std::cout << "NaN found in field " << name << std::endl;
+                    std::exit(1);
+                }
+                int w = std::fprintf(fp, "%i, ", i);
+                if (dim >= 2 && w >= 0) w = std::fprintf(fp, "%i, ", j);
+                if (dim >= 3 && w >= 0) w = std::fprintf(fp, "%i, ", k);
+                if (w >= 0) w = std::fprintf(fp, vf.c_str(), v);
+                if (w < 0) {
+                    std::cout << "Error writing data to output file " << path << std::endl;
+                    std::exit(1);
+                }
+            }
+    std::fclose(fp);
+}
+
+int field::addImplicitString(const std::string &s) {
+    implicit_prefactor_strings.push_back(s);
+    return 0;
+}
+
+void field::printImplicitString() {
+    for (const std::string &s : implicit_prefactor_strings) std::cout << s << std::endl;
+    for (const auto &kv : usedParameters) std::cout << kv.first << " " << kv.second << std::endl;
+}
+
+// Re-parse the stored prefactor strings of everything that mentions `name`
+// (/root/reference/src/field.cpp:422-441); the evolver re-bakes the plan constants afterwards.
+int field::updateParameter(const std::string &name, float) {
+    if (usedParameters[name]) system_p->_parser->recalculateImplicits(implicit_prefactor_strings, implicit, dynamic ? 1 : 0);
+    for (term *t : terms)
+        if (t->usedParameters[name]) system_p->_parser->recalculateImplicits(t->prefactor_strings, t->prefactors_h, 0);
+    return 0;
+}
