@@ -55,7 +55,73 @@ _SIGS = {
     "cupss_capi_dump_plan": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
 }
 
+# entry points that only the product build of the facade exports (tools/cupss_capi.h, CUPSS_B200_PRODUCT)
+_PRODUCT_SIGS = {
+    "cupss_capi_engine_plan": (C.c_void_p, [C.c_void_p]),
+    "cupss_capi_set_noise_seed": (None, [C.c_void_p, C.c_ulonglong]),
+    "cupss_capi_set_partition": (None, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+}
+
+# the engine's C ABI (include/cupss_b200.h): only the measurement / multi-GPU hooks are bound here,
+# the rest is reached through the C++ evolver exactly like a user's main() would
+ENGINE_LIB = os.path.join(REPO_ROOT, "cupss_b200", "lib", "libcupss_b200.so")
+_ENGINE_SIGS = {
+    "cupss_b200_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "cupss_b200_destroy": (None, [C.c_void_p]),
+    "cupss_b200_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "cupss_b200_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "cupss_b200_add_field": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "cupss_b200_set_implicit": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Pres), C.c_int]),
+    "cupss_b200_clear_terms": (C.c_int, [C.c_void_p, C.c_int]),
+    "cupss_b200_add_term": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Pres), C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "cupss_b200_set_noise": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Pres), C.c_ulonglong]),
+    "cupss_b200_set_dealias_rule": (C.c_int, [C.c_void_p, C.c_int]),
+    "cupss_b200_finalize": (C.c_int, [C.c_void_p]),
+    "cupss_b200_upload_real": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cupss_b200_download_real": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cupss_b200_download_comp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cupss_b200_step": (C.c_int, [C.c_void_p, C.c_int]),
+    "cupss_b200_sync": (C.c_int, [C.c_void_p]),
+    "cupss_b200_field_alias": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cupss_b200_time_steps": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "cupss_b200_profile_step": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "cupss_b200_launches_per_step": (C.c_int, [C.c_void_p]),
+    "cupss_b200_bytes_per_step": (C.c_double, [C.c_void_p]),
+    "cupss_b200_comm_bytes_per_step": (C.c_double, [C.c_void_p]),
+    "cupss_b200_device_spectrum": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "cupss_b200_last_error": (C.c_char_p, []),
+}
+
 _LIBS: dict[str, C.CDLL] = {}
+_ENGINE = None
+
+
+def load_engine() -> C.CDLL:
+    """dlopen the CUDA engine (C ABI).  Fails loudly if it has not been built: there is no fallback."""
+    global _ENGINE
+    if _ENGINE is None:
+        if not os.path.exists(ENGINE_LIB):
+            raise FileNotFoundError(f"{ENGINE_LIB} not found -- run __graft_entry__.build() first; the CUDA engine has no CPU fallback")
+        lib = C.CDLL(ENGINE_LIB, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _ENGINE_SIGS.items():
+            fn = getattr(lib, name)   # AttributeError if the library does not export what include/cupss_b200.h declares
+            fn.restype = res
+            fn.argtypes = args
+        _ENGINE = lib
+    return _ENGINE
+
+
+def engine_symbols():
+    return sorted(_ENGINE_SIGS)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def engine_check(code: int, what: str = ""):
+    if code != 0:
+        raise EngineError(f"{what}: {load_engine().cupss_b200_last_error().decode()} (code {code})")
 
 
 def load_facade(path: str) -> C.CDLL:
@@ -71,6 +137,11 @@ def load_facade(path: str) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in _PRODUCT_SIGS.items():
+        fn = getattr(lib, name, None)   # absent from the oracle builds
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     _LIBS[path] = lib
     return lib
 
@@ -97,6 +168,43 @@ class Evolver:
             self.close()
         except Exception:
             pass
+
+    # --- B200 engine access (product library only) ---------------------------
+    def enginePlan(self):
+        return self._lib.cupss_capi_engine_plan(self._h)
+
+    def setNoiseSeed(self, seed: int):
+        self._lib.cupss_capi_set_noise_seed(self._h, int(seed))
+
+    def setPartition(self, rank: int, nranks: int, nccl_id: bytes):
+        self._lib.cupss_capi_set_partition(self._h, int(rank), int(nranks), nccl_id)
+
+    def timeSteps(self, nsteps: int) -> float:
+        """Run ``nsteps`` steps and return the CUDA-event time (ms) measured on the engine's own stream."""
+        ms = C.c_float(0)
+        engine_check(load_engine().cupss_b200_time_steps(self.enginePlan(), int(nsteps), C.byref(ms)), "time_steps")
+        return float(ms.value)
+
+    def profileStep(self):
+        """One step with an event after every launch: [(name, ms, algorithmic_bytes)]."""
+        n = C.c_int(0)
+        names = C.create_string_buffer(64 * 64)
+        ms = (C.c_float * 64)()
+        by = (C.c_double * 64)()
+        engine_check(load_engine().cupss_b200_profile_step(self.enginePlan(), 64, names, ms, by, C.byref(n)), "profile_step")
+        return [(names.raw[64 * i:64 * i + 64].split(b"\0")[0].decode(), float(ms[i]), float(by[i])) for i in range(n.value)]
+
+    def launchesPerStep(self) -> int:
+        return load_engine().cupss_b200_launches_per_step(self.enginePlan())
+
+    def bytesPerStep(self) -> float:
+        return load_engine().cupss_b200_bytes_per_step(self.enginePlan())
+
+    def commBytesPerStep(self) -> float:
+        return load_engine().cupss_b200_comm_bytes_per_step(self.enginePlan())
+
+    def sync(self):
+        engine_check(load_engine().cupss_b200_sync(self.enginePlan()), "sync")
 
     # --- system declaration -------------------------------------------------
     def createField(self, name: str, dynamic: bool) -> int:

@@ -577,6 +577,28 @@ struct cupss_b200_plan {
             ks.nout++;
         }
         ks.hasInv = invField >= 0 ? 1 : 0;
+        // lean evaluator when the sweep is a single noise-free dynamic field whose prefactors depend on q^2 only
+        ks.fastKind = KS_GENERIC;
+        if (ks.nout == 1 && ks.out[0].dynamic && !ks.out[0].noisy && ks.nsrc == 1 && extraInv.empty() && nterm <= 1 &&
+            ks.out[0].nimp <= 4 && !getenv("CUPSS_B200_GENERIC_KSTAGE")) {
+            bool ok = true;
+            for (int i = 0; i < npres; ++i)
+                if (ks.pres[i].iqx || ks.pres[i].iqy || ks.pres[i].iqz || ks.pres[i].invq || ks.pres[i].q2n < 0 || ks.pres[i].q2n > 3) ok = false;
+            if (nterm == 1 && (ks.term[0].mulI || ks.term[0].src > 0 || ks.term[0].npres > 3)) ok = false;
+            if (ok) {
+                ScalarQ2D& q = ks.sq2;
+                q = ScalarQ2D{};
+                q.hasTerm = (signed char)nterm;
+                if (nterm == 1) {
+                    q.ntp = ks.term[0].npres;
+                    q.termFused = ks.term[0].src < 0 ? 1 : 0;
+                    for (int i = 0; i < q.ntp; ++i) { q.tpre[i] = (double)ks.pres[ks.term[0].presOff + i].pre; q.tn[i] = ks.pres[ks.term[0].presOff + i].q2n; }
+                }
+                q.nimp = ks.out[0].nimp;
+                for (int i = 0; i < q.nimp; ++i) { q.ipre[i] = (double)ks.pres[ks.out[0].impOff + i].pre; q.in[i] = ks.pres[ks.out[0].impOff + i].q2n; }
+                ks.fastKind = KS_SCALAR_Q2;
+            }
+        }
         float2* invOut = nullptr;
         if (ks.hasInv) {
             if (dim == 3) CKR(get_scratch(sc++, &invOut)); else invOut = fields[invField].W2;

@@ -31,6 +31,7 @@ template <int L> struct AxisCfg {
     static constexpr int PADR = C < 16 ? FftPlan<L>::R0 : 0;
     static constexpr int ROWS = PADR > 0 ? L + L / PADR + 1 : L;
     static constexpr int THREADS = FftPlan<L>::T * C;
+    static constexpr int MINB = THREADS >= 512 ? 1 : 512 / THREADS;   // cap registers at 128/thread: >= 16 warps per SM
     static constexpr size_t SMEM = FftPlan<L>::R1 > 1 ? (size_t)ROWS * C * sizeof(float2) : 0;
 };
 
@@ -39,7 +40,7 @@ __device__ __forceinline__ long long axis_off(const AxisAddr& a, int b, int row,
 }
 
 template <int L, int DIR>
-__global__ void __launch_bounds__(AxisCfg<L>::THREADS) axis_plain_kernel(const __grid_constant__ AxisArgs a) {
+__global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_plain_kernel(const __grid_constant__ AxisArgs a) {
     using P = FftPlan<L>;
     constexpr int E = P::E, T = P::T, C = AxisCfg<L>::C;
     extern __shared__ float2 smem[];
@@ -68,8 +69,8 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS) axis_plain_kernel(const _
     }
 }
 
-template <int L>
-__global__ void __launch_bounds__(AxisCfg<L>::THREADS)
+template <int L, int KIND>
+__global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB)
 axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
     using P = FftPlan<L>;
     constexpr int E = P::E, T = P::T, C = AxisCfg<L>::C;
@@ -85,24 +86,84 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
 #pragma unroll
         for (int e = 0; e < E; ++e)
             v[e] = valid ? __ldg(a.in + axis_off(a.ain, b, t + T * e, col)) : make_float2(0.0f, 0.0f);
+        if (KIND == KS_SCALAR_Q2 && c == 0) {
+            // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ks.src[0] + axis_off(a.aout, b, t + T * e, col)));
+        }
         fft_line<L, -1>(v, t, a.tw, ex);
     } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = make_float2(0.0f, 0.0f);
     }
 
-    const unsigned int step = ks.stepCounter ? *ks.stepCounter : 0u;
+    // fixed (per thread) part of the mode index: column = kx, and ky for a z pass
+    const int iyFix = a.axis == 2 ? a.kyBase + b : 0;
+    if (KIND == KS_SCALAR_Q2) {
+        // Lean path.  The point loop is ROLLED (CH points per trip) to keep the kernel inside the instruction
+        // cache; the register array is rotated by CH after every trip so that all indices stay static.
+        const OutD& od = ks.out[0];
+        const int sRow = a.axis == 2 ? ks.sz : (a.axis == 1 ? ks.sy : 1);
+        const float stepRow = a.axis == 2 ? ks.stepqz : ks.stepqy;
+        const int cutRow = a.axis == 2 ? od.cutz : od.cuty;
+        const float qx = wavenumber(col, ks.sx, ks.stepqx);
+        const float qyFix = wavenumber(iyFix, ks.sy, ks.stepqy);
+        const float qx2 = CUPSS_FMUL(qx, qx);
+        const float qyFix2 = CUPSS_FMUL(qyFix, qyFix);
+        const bool fixSelf = ((col == 0) || (2 * col == ks.sx)) && ((iyFix == 0) || (2 * iyFix == ks.sy));
+        const int nyFix = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
+        const bool keepFix = od.inv && col <= od.cutx && (a.axis != 2 || nyFix <= od.cuty);
+        const long long rowStride = (long long)T * a.aout.rs;          // natural layout: consecutive e are T rows apart
+        const long long off0 = axis_off(a.aout, b, t, col);
+        const float2* sp = ks.src[0] + off0;
+        float2* dp = ks.dst[0] + off0;
+        constexpr int CH = E < 4 ? E : 4;
+        int row0 = t;
+#pragma unroll 1
+        for (int ch = 0; ch < E / CH; ++ch) {
+            float2 self[CH];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int row = t + T * e;
-        const int iy = a.axis == 2 ? a.kyBase + b : (a.axis == 1 ? row : 0);
-        const int iz = a.axis == 2 ? row : 0;
-        if (valid) {
-            const KPoint k = make_kpoint(ks, col, iy, iz);
-            // k-space arrays share the natural addressing of the pass output
-            v[e] = kstage_point(ks, k, v[e], axis_off(a.aout, b, row, col), step);
-        } else {
-            v[e] = make_float2(0.0f, 0.0f);
+            for (int j = 0; j < CH; ++j) self[j] = valid ? __ldcg(sp + j * rowStride) : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int row = row0 + T * j;
+                const float qr = wavenumber(row, sRow, stepRow);
+                const float qr2 = CUPSS_FMUL(qr, qr);
+                const float q2 = CUPSS_FADD(CUPSS_FADD(qx2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
+                float2 val = kstage_point_scalar_q2(ks.sq2, ks.dt, q2, v[j], self[j]);
+                if (fixSelf && ((row == 0) || (2 * row == sRow))) val.y = 0.0f;
+                if (valid) dp[j * rowStride] = val;
+                const int nr = row > sRow / 2 ? sRow - row : row;
+                v[j] = (keepFix && nr <= cutRow) ? val : make_float2(0.0f, 0.0f);
+            }
+            if (E > CH) {   // rotate: v[i] <- v[i + CH]
+                float2 tmp[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) tmp[j] = v[j];
+#pragma unroll
+                for (int i2 = 0; i2 < E - CH; ++i2) v[i2] = v[i2 + CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[E - CH + j] = tmp[j];
+            }
+            row0 += T * CH;
+            sp += CH * rowStride;
+            dp += CH * rowStride;
+        }
+    } else {
+        const unsigned int step = ks.stepCounter ? *ks.stepCounter : 0u;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int row = t + T * e;
+            const int iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0);
+            const int iz = a.axis == 2 ? row : 0;
+            if (valid) {
+                const KPoint k = make_kpoint(ks, col, iy, iz);
+                // k-space arrays share the natural addressing of the pass output
+                v[e] = kstage_point(ks, k, v[e], axis_off(a.aout, b, row, col), step);
+            } else {
+                v[e] = make_float2(0.0f, 0.0f);
+            }
         }
     }
 
@@ -142,13 +203,16 @@ static cudaError_t launch_kstage_L(const AxisArgs& a, const KStageD& ks, cudaStr
     static bool attr = false;
     if (!attr) {
         if (AxisCfg<L>::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(axis_kstage_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
-    axis_kstage_kernel<L><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+    if (ks.fastKind == KS_SCALAR_Q2) axis_kstage_kernel<L, KS_SCALAR_Q2><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+    else axis_kstage_kernel<L, KS_GENERIC><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
     return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <ctime>
+#include <cstring>
 #include <iomanip>
 
 #include "../../inc/cupss.h"
@@ -71,6 +72,16 @@ field *evolver::findField(const std::string &name, const char *who) {
         std::exit(1);
     }
     return it->second;
+}
+
+void evolver::setPartition(int rank, int nranks, const void *id) {
+    if (plan) {
+        std::cout << "ERROR: setPartition must be called before prepareProblem" << std::endl;
+        std::exit(1);
+    }
+    partRank = rank;
+    partRanks = nranks;
+    if (id) memcpy(partId, id, 128);
 }
 
 int evolver::createFromFile(const std::string &path) {
@@ -208,6 +219,7 @@ void evolver::prepareProblem() {
     if (verbose) std::cout << "Preparing problem." << std::endl;
     if (!plan) {
         engineCheck(cupss_b200_create(&plan, sx, sy, sz, dx, dy, dz, dt), "create");
+        if (partRanks > 1) engineCheck(cupss_b200_set_partition(plan, partRank, partRanks, partId), "set_partition");
         for (field *f : fields) {
             const int id = cupss_b200_add_field(plan, f->name.c_str(), f->dynamic ? 1 : 0);
             if (id < 0) engineCheck(-id, "add_field");
@@ -225,7 +237,8 @@ void evolver::prepareProblem() {
     if (verbose) std::cout << "Copying initial states to device." << std::endl;
     for (field *f : fields) {
         for (term *t : f->terms) t->prepareDevice();
-        engineCheck(cupss_b200_upload_real(plan, f->engine_id, reinterpret_cast<const float *>(f->real_array)), "upload_real");
+        const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;   // this rank's z-slab of the full host array
+        engineCheck(cupss_b200_upload_real(plan, f->engine_id, reinterpret_cast<const float *>(f->real_array + slab)), "upload_real");
     }
     if (verbose) std::cout << "Building the fused per-equation plan." << std::endl;
     sendSystemToEngine();
@@ -257,8 +270,9 @@ int evolver::advanceTime() {
 
 void evolver::refreshHostMirror(field *f, bool real_part, bool comp_part) {
     if (!plan || f->engine_id < 0) return;
-    if (real_part) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array)), "download_real");
-    if (comp_part) engineCheck(cupss_b200_download_comp(plan, f->engine_id, reinterpret_cast<float *>(f->comp_array)), "download_comp");
+    const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;
+    if (real_part) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array + slab)), "download_real");
+    if (comp_part && partRanks == 1) engineCheck(cupss_b200_download_comp(plan, f->engine_id, reinterpret_cast<float *>(f->comp_array)), "download_comp");
 }
 
 void evolver::writeOut() {

@@ -82,6 +82,9 @@ class evolver {
     void setNoiseSeed(unsigned long long seed) { noiseSeed = seed; seedFixed = true; }
     void refreshHostMirror(field *f, bool real_part, bool comp_part);
     void markPlanDirty() { planDirty = true; }
+    // Slab partition over `nranks` processes (one GPU each); 3-D only.  Host arrays stay full-size, each
+    // rank reads/writes only its own z-slab [rank*sz/nranks, (rank+1)*sz/nranks).  Call before prepareProblem.
+    void setPartition(int rank, int nranks, const void *nccl_unique_id_128);
 
    private:
     const int sx, sy, sz;
@@ -96,6 +99,8 @@ class evolver {
     bool planDirty = true;
     unsigned long long noiseSeed = 0;
     bool seedFixed = false;
+    int partRank = 0, partRanks = 1;
+    char partId[128] = {0};
     void sendSystemToEngine();   // implicit + terms + noise of every field -> C ABI, then finalize
     void engineCheck(int code, const char *what);
     field *findField(const std::string &name, const char *who);

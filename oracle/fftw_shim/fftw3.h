@@ -37,6 +37,10 @@ void fftwf_destroy_plan(fftwf_plan p);
  * like the serial reference; the bench's CPU arm raises it and says so). */
 void cupss_shim_set_threads(int n);
 int cupss_shim_get_threads(void);
+/* shim-only knob: 1 (default) = double arithmetic inside each transform (float in/out, one rounding);
+ * 0 = float arithmetic throughout, like libfftw3f. */
+void cupss_shim_set_double(int on);
+int cupss_shim_get_double(void);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,15 @@ void *cupss_capi_create(int with_cuda, int sx, int sy, int sz, float dx, float d
 
 void cupss_capi_destroy(void *ev) { delete EV(ev); }
 
-int cupss_capi_create_field(void *ev, const char *name, int dynamic) { return EV(ev)->createField(name, dynamic != 0); }
+int cupss_capi_create_field(void *ev, const char *name, int dynamic)
+{
+    int r = EV(ev)->createField(name, dynamic != 0);
+    /* field::integrator is never initialised by the reference (inc/cupss/field.h:53, SURVEY.md 8c hazard 7);
+     * a user can and must set the public member, otherwise the CPU path may print "RK2 not implemented"
+     * instead of stepping. */
+    if (r == 0) EV(ev)->fieldsMap[name]->integrator = EULER;
+    return r;
+}
 int cupss_capi_add_parameter(void *ev, const char *name, float value) { return EV(ev)->addParameter(name, value); }
 int cupss_capi_add_equation(void *ev, const char *equation) { return EV(ev)->addEquation(equation); }
 int cupss_capi_add_noise(void *ev, const char *field, const char *expr) { return EV(ev)->addNoise(field, expr); }
@@ -134,5 +142,11 @@ int cupss_capi_dump_plan(void *ev, char *buf, int buflen)
     std::memcpy(buf, s.c_str(), s.size() + 1);
     return (int)s.size();
 }
+
+#ifdef CUPSS_B200_PRODUCT
+void *cupss_capi_engine_plan(void *ev) { return EV(ev)->enginePlan(); }
+void cupss_capi_set_noise_seed(void *ev, unsigned long long seed) { EV(ev)->setNoiseSeed(seed); }
+void cupss_capi_set_partition(void *ev, int rank, int nranks, const void *id) { EV(ev)->setPartition(rank, nranks, id); }
+#endif
 
 } /* extern "C" */

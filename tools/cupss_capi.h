@@ -46,6 +46,12 @@ void cupss_capi_initialize_from_file(void *ev, const char *name, const char *pat
 /* textual dump of the parsed system from public members (fields, implicit pres, terms, products, noise, aliasing) */
 int cupss_capi_dump_plan(void *ev, char *buf, int buflen);
 
+
+/* ---- product build only (-DCUPSS_B200_PRODUCT): access to the engine behind the evolver ---- */
+void *cupss_capi_engine_plan(void *ev);                       /* cupss_b200_plan* (include/cupss_b200.h) */
+void cupss_capi_set_noise_seed(void *ev, unsigned long long seed);
+void cupss_capi_set_partition(void *ev, int rank, int nranks, const void *nccl_id128);
+
 #ifdef __cplusplus
 }
 #endif
