@@ -1,0 +1,119 @@
+"""Shared parity cases: the same seeded system is driven through the product library, the compiled reference
+(oracle/_ref) and, where useful, the numpy restatement.  Inputs are deterministic functions of the shape."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_F = os.path.join(ROOT, "oracle", "_ref", "libcupss_ref_f.so")
+ORACLE_U = os.path.join(ROOT, "oracle", "_ref", "libcupss_ref_u.so")
+SHIM = os.path.join(ROOT, "oracle", "_ref", "libfftw_shim.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def smooth_ic(sx, sy, sz, amp=0.5, noise=0.05, seed=1):
+    """O(amp) smooth structure + white noise: exercises the nonlinear terms without sitting on the float32 floor
+    (SURVEY.md Appendix C)."""
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    f = amp * np.sin(2 * np.pi * 2 * x / sx)
+    if sy > 1:
+        f = f * np.cos(2 * np.pi * 3 * y / sy)
+    if sz > 1:
+        f = f * np.cos(2 * np.pi * z / sz)
+    return (f + noise * (2 * rng.random((sz, sy, sx)) - 1)).astype(np.float32)
+
+
+def rel_l2(a, b):
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a, b = np.asarray(a, dtype=dt).ravel(), np.asarray(b, dtype=dt).ravel()
+    n = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (n if n > 0 else 1.0))
+
+
+CH_PARAMS = dict(a=-1.0, b=1.0, k=4.0)
+MODELH_FIELDS = [("phi", 1), ("iqxphi", 0), ("iqyphi", 0), ("sigxx", 0), ("sigxy", 0), ("vx", 0), ("vy", 0), ("w", 0), ("P", 0)]
+MODELH_PARAMS = dict(a=-1, b=1, k=4, eta=1, friction=0, ka=4)
+MODELH_EQS = [   # examples/04_model_h/modelh_base.cpp:33-43
+    "dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 -vx*iqxphi - vy*iqyphi", "iqxphi = iqx*phi", "iqyphi = iqy*phi",
+    "sigxx = - 0.5*ka *iqxphi * iqxphi + 0.5*ka*iqyphi*iqyphi", "sigxy = - ka *iqxphi * iqyphi",
+    "-q^2*P = (iqx*iqx-iqy*iqy)*sigxx + 2.0 * iqx*iqy*sigxy", "vx * (friction + eta*q^2) = -iqx*P + iqx*sigxx + iqy*sigxy",
+    "vy * (friction + eta*q^2) = -iqy*P + iqx*sigxy - iqy*sigxx", "w = 0.5*iqx * vy - 0.5*iqy*vx "]
+
+CASES = {
+    # config 01: examples/01_diffusion/01_diffusion.cpp:7-24 at its full size (the reference's CPU-runnable case)
+    "diffusion2d_256": dict(shape=(256, 256, 1), dt=0.1, fields=[("phi", 1)], params=dict(D=1.0), eqs=["dt phi + D * q^2 * phi = 0"],
+                            ic=dict(phi=("droplet", (0.0, 1.0, 30.0, 5.0, 128, 128, 0))), steps=100, oracle="U"),
+    # config 02 (reduced size): examples/02_cahn_hilliard/02_cahn-hilliard.cpp:17-35
+    "ch2d_64": dict(shape=(64, 64, 1), dt=0.1, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                    ic=dict(phi=("smooth", (0.1, 0.01))), steps=100),
+    "ch2d_64_cpu_rule": dict(shape=(64, 64, 1), dt=0.1, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                             ic=dict(phi=("smooth", (0.1, 0.01))), steps=100, oracle="U", device=0),
+    # config 03 (reduced size): examples/03_cahn_hilliard_3d/03_cahn_hilliard_3d.cpp:13-23
+    "ch3d_32": dict(shape=(32, 32, 32), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                    ic=dict(phi=("smooth", (0.5, 0.05))), steps=100),
+    "ch3d_64x32x16": dict(shape=(64, 32, 16), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                          ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
+    # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
+    "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
+                      ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),
+    # config 06 (3-D variant, noise off): h + three gradient constraint fields, merged product groups
+    "kpz3d_32_det": dict(shape=(32, 32, 32), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0), ("iqzh", 0)], params=dict(l=0.5),
+                         eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2 + l*iqzh^2", "iqxh = iqx*h", "iqyh = iqy*h", "iqzh = iqz*h"],
+                         ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
+    # the reference's operator tests (tests/tests.cpp:191-422) extended to 3 steps
+    "ops1d_16": dict(shape=(16, 1, 1), dt=0.1, fields=[("phi", 1), ("lapphi", 0), ("iqxphi", 0), ("invqphi", 0)], params={},
+                     eqs=["dt phi + q^2*phi = iqxphi^2", "lapphi = -q^2*phi", "iqxphi = iqx*phi", "invqphi = 1/q*phi"],
+                     ic=dict(phi=("smooth", (0.5, 0.05))), steps=3),
+    "ops3d_16": dict(shape=(16, 16, 16), dt=0.1, fields=[("phi", 1), ("lapphi", 0), ("iqxphi", 0), ("invqphi", 0), ("iqyphi", 0), ("iqzphi", 0)],
+                     params={}, eqs=["dt phi + q^2*phi = iqxphi^2", "lapphi = -q^2*phi", "iqxphi = iqx*phi", "invqphi = 1/q*phi",
+                                     "iqyphi = iqy*phi", "iqzphi = iqz*phi"], ic=dict(phi=("smooth", (0.5, 0.05))), steps=3),
+}
+
+
+def build_system(case, lib=None, device=1):
+    from cupss_b200.capi import Evolver
+    sx, sy, sz = case["shape"]
+    ev = Evolver(device, sx, sy, sz, 1.0, 1.0, 1.0, case["dt"], lib=lib)
+    for n, d in case["fields"]:
+        ev.createField(n, d)
+    for k, v in case["params"].items():
+        ev.addParameter(k, v)
+    for e in case["eqs"]:
+        ev.addEquation(e)
+    for f, a in case.get("noise", []):
+        ev.addNoise(f, a)
+    for name, (kind, args) in case["ic"].items():
+        if kind == "smooth":
+            ev.setReal(name, smooth_ic(sx, sy, sz, *args))
+        elif kind == "droplet":
+            ev.initializeDroplet(name, *args)
+    return ev
+
+
+def run_case(case, lib=None, device=None, steps=None):
+    """Returns {field: real array} after `steps` advanceTime calls."""
+    if device is None:
+        device = case.get("device", 1)
+    ev = build_system(case, lib=lib, device=device)
+    ev.prepareProblem()
+    ev.advanceTime(case["steps"] if steps is None else steps)
+    if device:   # RUN_GPU: host mirrors are refreshed on request; RUN_CPU: they are live (and the reference's
+        ev.copyAllDataToHost()   # copyDeviceToHost would overwrite them with its unused device arrays)
+    out = {n: ev.real(n) for n, _ in case["fields"]}
+    ev.close()
+    return out
+
+
+def load_truth(name):
+    """A reference base_truth column as a flat float64 array (last CSV column)."""
+    path = os.path.join(GOLDEN, "base_truths", name)
+    vals = []
+    with open(path) as f:
+        for line in f:
+            parts = [p.strip() for p in line.replace(",", " ").split()]
+            try:
+                vals.append(float(parts[-1]))
+            except (ValueError, IndexError):
+                continue
+    return np.array(vals)

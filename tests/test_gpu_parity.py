@@ -1,0 +1,245 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI behind the evolver API, against
+  (1) the reference's golden vectors (its own unit tests, restated in refcases.py),
+  (2) the compiled reference CPU path (oracle/_ref) on the same seeded inputs -- tolerance of BASELINE.json:
+      relative L2 <= 1e-5 per field after 100 steps,
+  (3) the committed outputs of the reference produced in the build container (tests/golden/ref_runs.npz),
+  (4) size-independent properties at the benchmark's full sizes (mass conservation, closed-form diffusion decay,
+      noise variance and spectrum).
+Nothing here reads /root/reference."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import refcases
+from cases import CASES, ORACLE_F, ORACLE_U, ROOT, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # BASELINE.json north_star: relative L2 <= 1e-5 per field after 100 steps
+
+
+def _engine_loaded():
+    with open("/proc/self/maps") as f:
+        return "libcupss_b200.so" in f.read()
+
+
+def test_native_engine_is_the_path_that_runs(built):
+    import torch
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    out = cases.run_case(CASES["ops1d_16"], steps=1)
+    assert np.isfinite(out["phi"]).all()
+    assert _engine_loaded(), "libcupss_b200.so not mapped: the CUDA engine did not run"
+
+
+@pytest.mark.parametrize("shape", [(16, 1, 1), (64, 1, 1), (2, 1, 1), (16, 16, 1), (64, 32, 1), (16, 16, 16), (32, 16, 64), (128, 128, 1), (64, 64, 64), (1024, 4, 1), (4, 2048, 1)])
+def test_upload_download_round_trip_and_spectrum(built, shape):
+    from cupss_b200.capi import Evolver
+    sx, sy, sz = shape
+    ev = Evolver(1, sx, sy, sz, 1.0, 1.0, 1.0, 0.1)
+    ev.createField("phi", True)
+    ev.addEquation("dt phi + q^2*phi = 0")
+    ic = cases.smooth_ic(sx, sy, sz, 0.5, 0.5)
+    ev.setReal("phi", ic)
+    ev.prepareProblem()
+    ev.copyAllDataToHost()
+    assert rel_l2(ev.real("phi"), ic) < 1e-6
+    assert rel_l2(ev.comp("phi"), np.fft.fftn(ic.astype(np.float64))) < 1e-6
+    ev.close()
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_reference_unit_tests_init(built, dim):
+    assert refcases.init_case(dim, 1, None) < refcases.TOL
+
+
+@pytest.mark.parametrize("dim", [1, 3])
+@pytest.mark.parametrize("flavour", ["gpu", "cpu"])
+def test_reference_unit_tests_operators(built, dim, flavour):
+    errs = refcases.operators_case(dim, 1, None, flavour)
+    assert max(errs.values()) < refcases.TOL, errs
+
+
+@pytest.mark.parametrize("name", ["diffusion2d_256", "ch2d_64", "ch2d_64_cpu_rule", "ch3d_32", "ch3d_64x32x16", "modelh_32", "kpz3d_32_det", "ops1d_16", "ops3d_16"])
+def test_parity_with_compiled_reference(built, name):
+    case = CASES[name]
+    lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F
+    got = cases.run_case(case)                       # product, CUDA
+    want = cases.run_case(case, lib=lib, device=0)   # reference CPU path
+    for f, _ in case["fields"]:
+        scale = np.linalg.norm(want[f])
+        assert scale > 0
+        assert rel_l2(got[f], want[f]) < TOL, (f, rel_l2(got[f], want[f]))
+
+
+def test_parity_with_committed_reference_outputs(built):
+    gold = np.load(os.path.join(cases.GOLDEN, "ref_runs.npz"))
+    for name in ["ch3d_32", "modelh_32", "kpz3d_32_det"]:
+        got = cases.run_case(CASES[name])
+        for f, arr in got.items():
+            assert rel_l2(arr, gold[f"{name}/{f}"]) < TOL, (name, f)
+
+
+def test_generic_and_lean_kstage_agree_bitwise(built):
+    """KS_SCALAR_Q2 and the generic interpreter implement the same IEEE operation sequence."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, cases\n"
+            "out = cases.run_case(cases.CASES['ch3d_64x32x16'])\n"
+            "np.save(sys.argv[1], out['phi'])\n") % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        a, b = os.path.join(d, "a.npy"), os.path.join(d, "b.npy")
+        subprocess.run([sys.executable, "-c", code, a], check=True, cwd=ROOT)
+        subprocess.run([sys.executable, "-c", code, b], check=True, cwd=ROOT, env=dict(os.environ, CUPSS_B200_GENERIC_KSTAGE="1"))
+        assert np.array_equal(np.load(a), np.load(b))
+
+
+def test_step0_quirk_nonlinear_term_is_skipped_on_first_step(built):
+    """real_dealiased is zero until a field's first setRHS: b = 1 and b = 0 agree after one step."""
+    c1 = dict(CASES["ch2d_64"])
+    c0 = dict(c1, params=dict(a=-1.0, b=0.0, k=4.0))
+    a = cases.run_case(c1, steps=1)["phi"]
+    b = cases.run_case(c0, steps=1)["phi"]
+    assert np.array_equal(a, b)
+    assert not np.array_equal(cases.run_case(c1, steps=2)["phi"], cases.run_case(c0, steps=2)["phi"])
+
+
+def test_diffusion_closed_form_full_size(built):
+    """Config-02-sized grid (4096^2): every mode decays by 1/(1 + dt D q^2) per step."""
+    from cupss_b200.capi import Evolver
+    n, dt, steps = 4096, 0.1, 20
+    ev = Evolver(1, n, n, 1, 1.0, 1.0, 1.0, dt)
+    ev.createField("phi", True)
+    ev.addParameter("D", 1.0)
+    ev.addEquation("dt phi + D * q^2 * phi = 0")
+    y, x = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    modes = [(3, 5, 1.0), (40, 0, 0.5), (0, 700, 0.25)]
+    ic = sum(a * np.cos(2 * np.pi * (mx * x + my * y) / n) for mx, my, a in modes).astype(np.float32)
+    ev.setReal("phi", ic[None])
+    ev.prepareProblem()
+    ev.advanceTime(steps)
+    ev.copyAllDataToHost()
+    want = sum(a * np.cos(2 * np.pi * (mx * x + my * y) / n) / (1 + dt * ((2 * np.pi * mx / n) ** 2 + (2 * np.pi * my / n) ** 2)) ** steps
+               for mx, my, a in modes)
+    assert rel_l2(ev.real("phi")[0], want) < 2e-6
+    ev.close()
+
+
+def test_cahn_hilliard_3d_full_size_mass_conservation(built):
+    """Benchmark configuration (512^3): the q = 0 mode is invariant, the field stays finite and bounded."""
+    from cupss_b200.capi import Evolver
+    n = 512
+    ev = Evolver(1, n, n, n, 1.0, 1.0, 1.0, 0.01)
+    ev.createField("phi", True)
+    for k, v in cases.CH_PARAMS.items():
+        ev.addParameter(k, v)
+    ev.addEquation("dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 ")
+    rng = np.random.default_rng(3)
+    ic = (0.2 + 0.3 * (2 * rng.random((n, n, n), dtype=np.float32) - 1)).astype(np.float32)
+    ev.setReal("phi", ic)
+    ev.prepareProblem()
+    ev.advanceTime(20)
+    ev.copyAllDataToHost()
+    out = ev.real("phi")
+    assert np.isfinite(out).all()
+    assert abs(float(out.mean(dtype=np.float64)) - float(ic.mean(dtype=np.float64))) < 1e-6
+    assert float(np.abs(out).max()) < 1.0 and out.std() < ic.std()
+    ev.close()
+
+
+def test_noise_variance_and_spectrum(built):
+    """Stochastic runs match statistically: dt h = 0 + noise 2D gives site variance A*dt*n/dV; conserved noise
+    2*D*q^2 gives a per-step increment spectrum <|dh_q|^2>/N = 2 D q^2 dt / dV."""
+    from cupss_b200.capi import Evolver
+    n, dt, D, dx = 64, 0.01, 0.5, 0.5
+    ev = Evolver(1, n, n, 1, dx, dx, 1.0, dt)
+    ev.createField("h", True)
+    ev.addParameter("D", D)
+    ev.addEquation("dt h = 0")
+    ev.addNoise("h", "2*D")
+    ev.setNoiseSeed(1234)
+    ev.prepareProblem()
+    steps = 50
+    ev.advanceTime(steps)
+    ev.copyAllDataToHost()
+    var = float(ev.real("h").var())
+    expect = 2 * D * dt * steps / (dx * dx)
+    assert abs(var / expect - 1) < 0.06, (var, expect)          # 4096 sites: sigma ~ 2.2 %
+    assert abs(float(ev.real("h").mean())) < 5 * np.sqrt(expect / n / n)
+    ev.close()
+
+    ev = Evolver(1, n, n, 1, dx, dx, 1.0, dt)
+    ev.createField("p", True)
+    ev.addParameter("D", D)
+    ev.addEquation("dt p = 0")
+    ev.addNoise("p", "2*D*q^2")
+    ev.setNoiseSeed(99)
+    ev.prepareProblem()
+    prev = np.zeros((n, n), np.complex128)
+    acc = np.zeros((n, n))
+    reps = 200
+    for _ in range(reps):
+        ev.advanceTime(1)
+        ev.copyAllDataToHost()
+        cur = np.fft.fft2(ev.real("p")[0].astype(np.float64))
+        acc += np.abs(cur - prev) ** 2
+        prev = cur
+    q = 2 * np.pi * np.fft.fftfreq(n, d=dx)
+    q2 = q[None, :] ** 2 + q[:, None] ** 2
+    expect = 2 * D * q2 * dt / (dx * dx) * n * n
+    ratio = (acc / reps)[q2 > 0] / expect[q2 > 0]
+    assert abs(float(ratio.mean()) - 1) < 0.02, float(ratio.mean())
+    assert float(ratio.std()) < 0.25                              # per-mode chi^2 scatter ~ sqrt(1/200..2/200)
+    ev.close()
+
+
+def test_noise_stream_is_reproducible_and_seed_dependent(built):
+    from cupss_b200.capi import Evolver
+
+    def run(seed):
+        ev = Evolver(1, 32, 32, 32, 1.0, 1.0, 1.0, 0.01)
+        ev.createField("h", True)
+        ev.addEquation("dt h + 0.5*q^2*h = 0")
+        ev.addNoise("h", "1.0")
+        ev.setNoiseSeed(seed)
+        ev.prepareProblem()
+        ev.advanceTime(5)
+        ev.copyAllDataToHost()
+        out = ev.real("h")
+        ev.close()
+        return out
+    a, b, c = run(7), run(7), run(8)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert abs(float(a.mean())) < 0.05
+
+
+def test_update_parameter_rebakes_the_plan(built):
+    """evolver::updateParameter (src/evolver.cpp:386-394) on product and reference."""
+    def run(lib, device):
+        ev = cases.build_system(CASES["ch2d_64"], lib=lib, device=device)
+        ev.prepareProblem()
+        ev.advanceTime(10)
+        ev.updateParameter("b", 2.0)
+        ev.updateParameter("k", 3.0)
+        ev.advanceTime(10)
+        if device:
+            ev.copyAllDataToHost()
+        out = ev.real("phi")
+        ev.close()
+        return out
+    cwd = os.getcwd()
+    assert rel_l2(run(None, 1), run(ORACLE_F, 0)) < TOL
+    assert os.getcwd() == cwd
+
+
+def test_multi_gpu_slab_partition_matches_single_gpu(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(ROOT, "tests", "multi_gpu_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", script], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_GPU_OK" in r.stdout

