@@ -63,6 +63,7 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 }  // namespace
@@ -85,6 +86,7 @@ static int load_nccl() {
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
+    SYM(AllGather, "ncclAllGather")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return CUPSS_B200_OK;
@@ -116,7 +118,7 @@ struct Field {
 };
 
 struct Launch {
-    enum Kind { XPASS, AXIS_PLAIN, AXIS_KSTAGE, A2A, BUMP } kind;
+    enum Kind { XPASS, AXIS_PLAIN, AXIS_KSTAGE, A2A, BUMP, XBAR } kind;
     char name[64];
     int L = 0, dir = 0, mode = 0;
     AxisArgs ax{};
@@ -126,6 +128,8 @@ struct Launch {
     float2* recv = nullptr;
     size_t chunk = 0;   // float2 per peer
     double bytes = 0;   // algorithmic HBM bytes (A2A: bytes sent)
+    double commBytes = 0;   // bytes this rank sends to other GPUs inside this launch (pushed exchange)
+    XBarrier xb{};
 };
 
 int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
@@ -153,6 +157,15 @@ struct cupss_b200_plan {
     bool useGraph = true;
     void* comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Peer-memory exchange arena (multi-GPU): [header: flags, epochs, error][slot 0][slot 1]...; every rank maps
+    // every peer's arena through CUDA IPC, and the y / z pass kernels store their output rows straight into the
+    // owner's slot over NVLink (no NCCL, no staging copy on the hot path).
+    bool useP2P = true;
+    float2* arena = nullptr;
+    size_t arenaSlots = 0;
+    float2* peerArena[CUPSS_MAX_PEERS] = {nullptr};
+    static constexpr size_t kArenaHeader = 4096;   // float2 elements (32 KiB)
+    int arenaNext = 0, nextPt = 0;
 
     // ------------------------------------------------------------ helpers
     int get_twiddle(int L, const float2** out) {
@@ -225,12 +238,68 @@ struct cupss_b200_plan {
         return CUPSS_B200_OK;
     }
 
+    float2* arena_slot_ptr(int peer, int slot) const {
+        return peerArena[peer] ? peerArena[peer] + kArenaHeader + (size_t)slot * specElems : nullptr;
+    }
+    // Collective: (re)allocate the arena with room for `nslots` receive buffers and map every peer's copy.
+    int ensure_arena(size_t nslots) {
+        if (arena && arenaSlots >= nslots) return CUPSS_B200_OK;
+        CK(cudaStreamSynchronize(stream));
+        for (int d = 0; d < nranks; ++d) {
+            if (d != rank && peerArena[d]) CK(cudaIpcCloseMemHandle(peerArena[d]));
+            peerArena[d] = nullptr;
+        }
+        if (arena) CK(cudaFree(arena));
+        arena = nullptr;
+        const size_t elems = kArenaHeader + nslots * specElems;
+        CK(cudaMalloc(&arena, elems * sizeof(float2)));
+        CK(cudaMemsetAsync(arena, 0, elems * sizeof(float2), stream));
+        cudaIpcMemHandle_t mine;
+        CK(cudaIpcGetMemHandle(&mine, arena));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+        char* dbuf = nullptr;
+        CK(cudaMalloc(&dbuf, 64 * (size_t)(nranks + 1)));
+        CK(cudaMemcpyAsync(dbuf, &mine, 64, cudaMemcpyHostToDevice, stream));
+        NK(g_nccl.AllGather(dbuf, dbuf + 64, 64, /*ncclChar*/ 0, comm, stream));
+        std::vector<cudaIpcMemHandle_t> all(nranks);
+        CK(cudaMemcpyAsync(all.data(), dbuf + 64, 64 * (size_t)nranks, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaFree(dbuf));
+        for (int d = 0; d < nranks; ++d) {
+            if (d == rank) { peerArena[d] = arena; continue; }
+            void* ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, all[d], cudaIpcMemLazyEnablePeerAccess));
+            peerArena[d] = static_cast<float2*>(ptr);
+        }
+        arenaSlots = nslots;
+        return CUPSS_B200_OK;
+    }
+    // Receive-side addressing of a pushed exchange: slot layout [src rank][z_local][ky_local][pitch].
+    void set_push(AxisArgs& a, int slot, bool rowsAreKy) {
+        a.pushOn = 1;
+        if (rowsAreKy) { a.pushShift = ilog2(kyl); a.pushMask = kyl - 1; a.pushRs = pitch; a.pushBs = (long long)kyl * pitch; }   // y pass: batch = z_local
+        else { a.pushShift = ilog2(zl); a.pushMask = zl - 1; a.pushRs = (long long)kyl * pitch; a.pushBs = pitch; }               // z pass: batch = ky_local
+        a.pushBase = (long long)kArenaHeader + (long long)slot * (long long)specElems + (long long)rank * zl * kyl * pitch;
+        for (int d = 0; d < CUPSS_MAX_PEERS; ++d) a.push[d] = d < nranks ? peerArena[d] : nullptr;
+    }
+    void add_barrier(std::vector<Launch>& out, const char* nm) {
+        Launch l{};
+        l.kind = Launch::XBAR;
+        snprintf(l.name, sizeof l.name, "%s", nm);
+        for (int d = 0; d < CUPSS_MAX_PEERS; ++d) l.xb.flags[d] = d < nranks ? reinterpret_cast<unsigned int*>(peerArena[d]) : nullptr;
+        l.xb.epoch = arena ? reinterpret_cast<unsigned int*>(arena) + 1024 : nullptr;
+        l.xb.error = arena ? reinterpret_cast<int*>(arena) + 2048 : nullptr;
+        l.xb.rank = rank; l.xb.nranks = nranks; l.xb.pt = nextPt++;
+        out.push_back(l);
+    }
+
     int run_launch(Launch& l) {
         switch (l.kind) {
             case Launch::XPASS: CK(launch_xpass(sx, l.mode, l.xa, stream)); break;
             case Launch::AXIS_PLAIN: CK(launch_axis_plain(l.L, l.dir, l.ax, stream)); break;
             case Launch::AXIS_KSTAGE: CK(launch_axis_kstage(l.L, l.ax, l.ks, stream)); break;
             case Launch::BUMP: CK(launch_bump_counter(stepCounter, stream)); break;
+            case Launch::XBAR: CK(launch_xgpu_barrier(l.xb, stream)); break;
             case Launch::A2A: {
                 NK(g_nccl.GroupStart());
                 for (int d = 0; d < nranks; ++d) {
@@ -470,6 +539,17 @@ struct cupss_b200_plan {
                 CKR(get_scratch(sc++, &w4));
                 y.ax.in = groupSpec[g]; y.ax.out = w4;
                 y.bytes = 2.0 * spec_bytes();
+                if (nranks > 1 && useP2P) {
+                    // fused exchange: the y pass stores each ky row straight into the owning peer's slot
+                    const int slot = arenaNext++;
+                    set_push(y.ax, slot, true);
+                    y.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+                    snprintf(y.name, sizeof y.name, "yfwd_push_%s", tag);
+                    out.push_back(y);
+                    add_barrier(out, "xbar_fwd");
+                    groupSpec[g] = arena_slot_ptr(rank, slot);
+                    continue;
+                }
                 out.push_back(y);
                 groupSpec[g] = w4;
                 if (nranks > 1) {
@@ -605,11 +685,24 @@ struct cupss_b200_plan {
         }
         k.ax.out = invOut ? invOut : fields[outs[0]].S;   // only its addressing is used when there is no fused inverse
         k.bytes = (double)(ks.hasFwd + ks.nsrc + ks.nout + ks.hasInv) * spec_bytes();
-        out.push_back(k);
+        const bool pushInv = nranks > 1 && useP2P && dim == 3;
+        std::vector<std::pair<int, float2*>> w1s;   // (field, input of its inverse y pass)
+        std::vector<int> pushed;                    // same order: 1 if that input already sits in the local arena slot
+        if (ks.hasInv && pushInv) {
+            const int slot = arenaNext++;
+            set_push(k.ax, slot, false);
+            k.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+            snprintf(k.name, sizeof k.name, "kstage_push_%s", tag);
+            out.push_back(k);
+            add_barrier(out, "xbar_inv");
+            w1s.push_back({invField, arena_slot_ptr(rank, slot)});
+            pushed.push_back(1);
+        } else {
+            out.push_back(k);
+            if (invField >= 0 && dim == 3) { w1s.push_back({invField, invOut}); pushed.push_back(0); }
+        }
 
         // ---- remaining inverse transforms of dealiased fields
-        std::vector<std::pair<int, float2*>> w1s;
-        if (invField >= 0 && dim == 3) w1s.push_back({invField, invOut});
         for (int f : extraInv) {
             Launch z{};
             z.kind = Launch::AXIS_PLAIN; z.dir = +1;
@@ -624,12 +717,24 @@ struct cupss_b200_plan {
             if (dim == 3) CKR(get_scratch(sc++, &w1));
             z.ax.out = w1;
             z.bytes = 2.0 * spec_bytes();
+            if (pushInv) {
+                const int slot = arenaNext++;
+                set_push(z.ax, slot, false);
+                z.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+                snprintf(z.name, sizeof z.name, "lastinv_push_%s", tag);
+                out.push_back(z);
+                add_barrier(out, "xbar_inv");
+                w1s.push_back({f, arena_slot_ptr(rank, slot)});
+                pushed.push_back(1);
+                continue;
+            }
             out.push_back(z);
-            if (dim == 3) w1s.push_back({f, w1});
+            if (dim == 3) { w1s.push_back({f, w1}); pushed.push_back(0); }
         }
-        for (auto& pr : w1s) {
+        for (size_t wi = 0; wi < w1s.size(); ++wi) {
+            auto& pr = w1s[wi];
             const float2* yin = pr.second;
-            if (nranks > 1) {
+            if (nranks > 1 && !pushed[wi]) {
                 float2* r;
                 CKR(get_scratch(sc++, &r));
                 CKR(add_a2a(out, "a2a_inv", pr.second, r));
@@ -673,7 +778,16 @@ struct cupss_b200_plan {
                 CK(cudaMemsetAsync(F.W2, 0, specElems * sizeof(float2), stream));   // real_dealiased starts at zero
             }
         }
+        if (nranks > 1 && useP2P) {
+            // dry run to count the receive slots, then (collectively) size the arena and build for real
+            std::vector<Launch> dry;
+            arenaNext = 0; nextPt = 0;
+            CKR(build_stage(false, dry));
+            CKR(build_stage(true, dry));
+            CKR(ensure_arena((size_t)arenaNext));
+        }
         step.clear();
+        arenaNext = 0; nextPt = 0;
         CKR(build_stage(false, step));
         CKR(build_stage(true, step));
         Launch b{};
@@ -755,6 +869,9 @@ void cupss_b200_destroy(cupss_b200_plan* p) {
     for (auto& kv : p->twiddles) cudaFree(kv.second);
     if (p->realBuf) cudaFree(p->realBuf);
     if (p->stepCounter) cudaFree(p->stepCounter);
+    for (int d = 0; d < p->nranks; ++d)
+        if (d != p->rank && p->peerArena[d]) cudaIpcCloseMemHandle(p->peerArena[d]);
+    if (p->arena) cudaFree(p->arena);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -779,6 +896,9 @@ int cupss_b200_set_partition(cupss_b200_plan* p, int rank, int nranks, const voi
     memcpy(uid.b, id, 128);
     NK(g_nccl.CommInitRank(&p->comm, nranks, uid, rank));
     p->rank = rank; p->nranks = nranks;
+    if (nranks > CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "at most %d ranks", CUPSS_MAX_PEERS);
+    const char* na = getenv("CUPSS_B200_NCCL_A2A");
+    p->useP2P = !(na && na[0] == '1');
     p->zl = p->sz / nranks; p->kyl = p->sy / nranks;
     p->specElems = (size_t)p->pitch * p->kyl * p->sz;   // == pitch * sy * zl
     return CUPSS_B200_OK;
@@ -914,6 +1034,11 @@ int cupss_b200_step(cupss_b200_plan* p, int nsteps) {
 int cupss_b200_sync(cupss_b200_plan* p) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
     CK(cudaStreamSynchronize(p->stream));
+    if (p->arena) {
+        int err = 0;
+        CK(cudaMemcpy(&err, reinterpret_cast<int*>(p->arena) + 2048, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(CUPSS_B200_ERR_COMM, "cross-GPU barrier timed out (a peer rank stopped)");
+    }
     return CUPSS_B200_OK;
 }
 
@@ -972,7 +1097,7 @@ double cupss_b200_bytes_per_step(cupss_b200_plan* p) {
 }
 double cupss_b200_comm_bytes_per_step(cupss_b200_plan* p) {
     double b = 0;
-    if (p) for (auto& l : p->step) if (l.kind == Launch::A2A) b += l.bytes;
+    if (p) for (auto& l : p->step) b += l.kind == Launch::A2A ? l.bytes : l.commBytes;
     return b;
 }
 void* cupss_b200_device_spectrum(cupss_b200_plan* p, int f) {

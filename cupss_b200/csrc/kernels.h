@@ -5,6 +5,8 @@
 
 namespace cupss {
 
+constexpr int CUPSS_MAX_PEERS = 8;
+
 // Addressing of one side (input or output) of a strided-axis pass.  Row r of batch b, column c:
 //   b*bs + (r >> rpcShift)*cs + (r & (rpc-1))*rs + c          (float2 elements)
 // Natural layouts use rpc = L (one chunk).  The multi-GPU exchange layout [peer][z_loc][ky_loc][kx]
@@ -26,6 +28,20 @@ struct AxisArgs {
     int kyBase;      // axis == 2: iky = kyBase + batch
     int maskOn, cutx, cuty, cutz;   // plain inverse: dealias mask applied on load
     int sx, sy, sz;
+    // Fused slab exchange (multi-GPU): instead of `out`, row r of batch b is stored straight into the receive
+    // buffer of peer (r >> pushShift) over NVLink:  push[peer] + pushBase + b*pushBs + (r & pushMask)*pushRs + col.
+    int pushOn, pushShift, pushMask;
+    long long pushRs, pushBs, pushBase;
+    float2* push[CUPSS_MAX_PEERS];
+};
+
+// Cross-GPU barrier after a pushed exchange: every rank bumps its epoch for exchange point `pt`, publishes it in
+// flag[pt][rank] of every peer (release.sys) and waits until all peers have published theirs (acquire.sys).
+struct XBarrier {
+    unsigned int* flags[CUPSS_MAX_PEERS];   // base of each peer's flag table [pt][CUPSS_MAX_PEERS]
+    unsigned int* epoch;                    // local epoch counters [pt]
+    int* error;                             // local: set to 1 on timeout
+    int rank, nranks, pt;
 };
 
 // x pass: C2R of up to XP_MAX_IN half-spectrum lines, real-space products, R2C of the results
@@ -62,6 +78,7 @@ cudaError_t launch_axis_plain(int L, int dir, const AxisArgs& a, cudaStream_t st
 cudaError_t launch_axis_kstage(int L, const AxisArgs& a, const KStageD& ks, cudaStream_t st);
 cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st);
 cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
+cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
 bool fft_size_supported(int n);
 

@@ -39,6 +39,13 @@ __device__ __forceinline__ long long axis_off(const AxisAddr& a, int b, int row,
     return (long long)b * a.bs + (long long)(row >> a.rpcShift) * a.cs + (long long)(row & a.rpcMask) * a.rs + col;
 }
 
+// Destination of row `row` of batch b: local array, or the receive buffer of the peer that owns the row.
+__device__ __forceinline__ float2* axis_dst(const AxisArgs& a, int b, int row, int col) {
+    if (a.pushOn)
+        return a.push[row >> a.pushShift] + a.pushBase + (long long)b * a.pushBs + (long long)(row & a.pushMask) * a.pushRs + col;
+    return a.out + axis_off(a.aout, b, row, col);
+}
+
 template <int L, int DIR>
 __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_plain_kernel(const __grid_constant__ AxisArgs a) {
     using P = FftPlan<L>;
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     fft_line<L, DIR>(v, t, a.tw, ex);
     if (valid) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+        for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
     }
 }
 
@@ -172,12 +179,36 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
         fft_line<L, +1>(v, t, a.tw, ex);
         if (valid) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+            for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
         }
     }
 }
 
 __global__ void bump_counter_kernel(unsigned int* c) { *c += 1u; }
+
+__global__ void xgpu_barrier_kernel(const XBarrier b) {
+    __shared__ unsigned int target;
+    if (threadIdx.x == 0) {
+        target = b.epoch[b.pt] + 1u;
+        b.epoch[b.pt] = target;
+    }
+    __syncthreads();
+    const int d = threadIdx.x;
+    if (d < b.nranks) {
+        // everything this GPU pushed in earlier kernels of the stream is ordered before the flag (cumulative fence)
+        __threadfence_system();
+        unsigned int* theirs = b.flags[d] + b.pt * CUPSS_MAX_PEERS + b.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(target) : "memory");
+        const unsigned int* mine = b.flags[b.rank] + b.pt * CUPSS_MAX_PEERS + d;
+        const long long t0 = clock64();
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if (clock64() - t0 > 6000000000LL) { *b.error = 1; break; }   // ~3 s: a peer died; do not hang the GPU
+        } while ((int)(seen - target) < 0);
+        __threadfence_system();
+    }
+}
 
 // ---------------------------------------------------------------- dispatch
 template <int L>
@@ -246,6 +277,11 @@ int axis_tile_cols(int L) {
 }
 
 bool fft_size_supported(int n) { return axis_tile_cols(n) != 0; }
+
+cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st) {
+    xgpu_barrier_kernel<<<1, 32, 0, st>>>(b);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st) {
     bump_counter_kernel<<<1, 1, 0, st>>>(counter);
