@@ -16,6 +16,7 @@
 // "y-inverse done" half spectra W2 = [sz_local][sy][pitch] which the x pass turns into real lines
 // on chip.  W2 starts at zero, which reproduces the reference's step-0 behaviour (real_dealiased is
 // zero until a field's first setRHS).
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -115,6 +116,7 @@ struct Field {
     int aliasOrder = 1;
     float2* S = nullptr;    // spectrum
     float2* W2 = nullptr;   // dealiased field, y-inverse done
+    int w2cut[3] = {-1, -1, -1};   // cut-offs W2 was pruned with (pruned regions rely on staying zero)
 };
 
 struct Launch {
@@ -155,6 +157,7 @@ struct cupss_b200_plan {
     cudaGraphExec_t graphExec = nullptr;
     bool finalized = false;
     bool useGraph = true;
+    bool prune = true;     // skip the parts of inverse transforms that the dealias mask makes identically zero
     void* comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // Peer-memory exchange arena (multi-GPU): [header: flags, epochs, error][slot 0][slot 1]...; every rank maps
@@ -201,6 +204,7 @@ struct cupss_b200_plan {
         a.ncolTiles = (ncol + axis_tile_cols(L) - 1) / axis_tile_cols(L);
         a.sx = sx; a.sy = sy; a.sz = sz;
         a.maskOn = 0; a.cutx = a.cuty = a.cutz = 0;
+        a.pruneOn = 0; a.pruneCutX = a.pruneCutY = 0; a.rowCut = -1;
         a.kyBase = rank * kyl;
     }
     // last axis of the transform: z in 3-D (rows kz, batch ky_local), y in 2-D, nothing in 1-D
@@ -387,6 +391,7 @@ struct cupss_b200_plan {
         x.kind = Launch::XPASS; x.mode = X_C2R_ONLY;
         x.xa.nIn = 1; x.xa.nOut = 0; x.xa.nMono = 0;
         x.xa.in[0] = xin;
+        x.xa.kmax[0] = ncol - 1;
         x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
         x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
         x.xa.realOut = realBuf;
@@ -499,10 +504,15 @@ struct cupss_b200_plan {
                     CK(cudaMemsetAsync(F0.W2, 0, specElems * sizeof(float2), stream));
                 }
             }
+            double inFrac = 0.0;
             for (size_t i = 0; i < ins.size(); ++i) {
                 Field& F = fields[ins[i]];
                 if (!F.W2) return fail(CUPSS_B200_ERR_STATE, "internal: field %s has no dealiased buffer", F.name.c_str());
                 x.xa.in[i] = F.W2;
+                short cx, cy, cz;
+                cutoffs(F.aliasOrder, &cx, &cy, &cz);
+                x.xa.kmax[i] = prune ? (cx < ncol - 1 ? cx : ncol - 1) : ncol - 1;
+                inFrac += (double)(x.xa.kmax[i] + 1) / ncol;
             }
             x.xa.nOut = (int)(g1 - g0);
             int mi = 0;
@@ -523,7 +533,7 @@ struct cupss_b200_plan {
             x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
             x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
             CKR(get_twiddle(sx, &x.xa.tw));
-            x.bytes = (double)(x.xa.nIn + x.xa.nOut) * spec_bytes();
+            x.bytes = (inFrac + x.xa.nOut) * spec_bytes();
             out.push_back(x);
             g0 = g1;
         }
@@ -685,6 +695,15 @@ struct cupss_b200_plan {
         }
         k.ax.out = invOut ? invOut : fields[outs[0]].S;   // only its addressing is used when there is no fused inverse
         k.bytes = (double)(ks.hasFwd + ks.nsrc + ks.nout + ks.hasInv) * spec_bytes();
+        if (ks.hasInv && prune) {
+            short cx, cy, cz;
+            cutoffs(fields[invField].aliasOrder, &cx, &cy, &cz);
+            k.ax.pruneOn = 1; k.ax.pruneCutX = cx; k.ax.pruneCutY = cy;
+            const int C = axis_tile_cols(k.L);
+            const double fx = (double)std::min(ncol, (cx / C + 1) * C) / ncol;
+            const double fy = dim == 3 ? std::min(1.0, (2.0 * cy + 1.0) / sy) : 1.0;
+            k.bytes = (double)(ks.hasFwd + ks.nsrc + ks.nout) * spec_bytes() + fx * fy * spec_bytes();
+        }
         const bool pushInv = nranks > 1 && useP2P && dim == 3;
         std::vector<std::pair<int, float2*>> w1s;   // (field, input of its inverse y pass)
         std::vector<int> pushed;                    // same order: 1 if that input already sits in the local arena slot
@@ -712,6 +731,10 @@ struct cupss_b200_plan {
             short cx, cy, cz;
             cutoffs(fields[f].aliasOrder, &cx, &cy, &cz);
             z.ax.cutx = cx; z.ax.cuty = cy; z.ax.cutz = cz;
+            if (prune) {
+                z.ax.pruneOn = 1; z.ax.pruneCutX = cx; z.ax.pruneCutY = cy;
+                z.ax.rowCut = dim == 3 ? (cz < z.L ? cz : -1) : (cy < z.L ? cy : -1);
+            }
             z.ax.in = fields[f].S;
             float2* w1 = fields[f].W2;
             if (dim == 3) CKR(get_scratch(sc++, &w1));
@@ -746,6 +769,15 @@ struct cupss_b200_plan {
             CKR(make_y_axis(y.ax, false));
             y.ax.in = yin; y.ax.out = fields[pr.first].W2;
             y.bytes = 2.0 * spec_bytes();
+            if (prune) {
+                short cx, cy, cz;
+                cutoffs(fields[pr.first].aliasOrder, &cx, &cy, &cz);
+                const int C = axis_tile_cols(sy);
+                y.ax.pruneOn = 1; y.ax.pruneCutX = cx; y.ax.pruneCutY = 32767;   // batch is z here: never pruned
+                y.ax.rowCut = cy < sy ? cy : -1;
+                const double fx = (double)std::min(ncol, (cx / C + 1) * C) / ncol;
+                y.bytes = fx * spec_bytes() * (1.0 + std::min(1.0, (2.0 * cy + 1.0) / sy));
+            }
             out.push_back(y);
         }
         return CUPSS_B200_OK;
@@ -776,6 +808,14 @@ struct cupss_b200_plan {
             if (F.needsAlias && !F.W2) {
                 CK(cudaMalloc(&F.W2, specElems * sizeof(float2)));
                 CK(cudaMemsetAsync(F.W2, 0, specElems * sizeof(float2), stream));   // real_dealiased starts at zero
+            }
+            if (F.needsAlias) {
+                short cx, cy, cz;
+                cutoffs(F.aliasOrder, &cx, &cy, &cz);
+                const int now[3] = {prune ? cx : -2, prune ? cy : -2, prune ? cz : -2};
+                if (F.w2cut[0] != -1 && (now[0] != F.w2cut[0] || now[1] != F.w2cut[1] || now[2] != F.w2cut[2]))
+                    CK(cudaMemsetAsync(F.W2, 0, specElems * sizeof(float2), stream));   // pruned regions must read as zero
+                F.w2cut[0] = now[0]; F.w2cut[1] = now[1]; F.w2cut[2] = now[2];
             }
         }
         if (nranks > 1 && useP2P) {
@@ -851,6 +891,8 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     p->specElems = (size_t)p->pitch * sy * sz;
     const char* ng = getenv("CUPSS_B200_NO_GRAPH");
     p->useGraph = !(ng && ng[0] == '1');
+    const char* np_ = getenv("CUPSS_B200_NO_PRUNE");
+    p->prune = !(np_ && np_[0] == '1');
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));

@@ -28,6 +28,12 @@ struct AxisArgs {
     int kyBase;      // axis == 2: iky = kyBase + batch
     int maskOn, cutx, cuty, cutz;   // plain inverse: dealias mask applied on load
     int sx, sy, sz;
+    // Dealias-aware pruning of inverse transforms: a dealiased spectrum is zero outside |n_a| <= cut_a, so
+    //  * a tile whose columns all lie beyond pruneCutX (or whose fixed ky lies beyond pruneCutY) is skipped
+    //    entirely -- its output is never written and stays at its initial zero;
+    //  * rows of the transformed axis beyond rowCut are known zeros and are not loaded (rowCut < 0: off).
+    int pruneOn, pruneCutX, pruneCutY;
+    int rowCut;
     // Fused slab exchange (multi-GPU): instead of `out`, row r of batch b is stored straight into the receive
     // buffer of peer (r >> pushShift) over NVLink:  push[peer] + pushBase + b*pushBs + (r & pushMask)*pushRs + col.
     int pushOn, pushShift, pushMask;
@@ -69,6 +75,7 @@ struct XArgs {
     const float* realIn;   // mode R2C_ONLY
     int jobsPerCta;
     int perJobFloat2;      // shared-memory float2 per job
+    int kmax[XP_MAX_IN];   // input g is zero for kx > kmax[g] (dealias cut-off): those points are not loaded
 };
 
 enum XMode { X_HOT = 0, X_C2R_ONLY = 1, X_R2C_ONLY = 2 };

@@ -57,11 +57,21 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     const bool valid = col < a.ncol;
     TileEx<C, AxisCfg<L>::PADR> ex{smem, c};
 
+    if (a.pruneOn) {   // CTA-uniform: the whole tile is outside the dealias cut-off -> output stays zero
+        const int iyT = a.kyBase + b;
+        const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
+        if (ct * C > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
+    }
+
     float2 v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int row = t + T * e;
         bool keep = valid;
+        if (a.rowCut >= 0) {
+            const int nr = row > L / 2 ? L - row : row;
+            keep = keep && nr <= a.rowCut;
+        }
         if (a.maskOn) {
             const int iy = a.axis == 2 ? a.kyBase + b : (a.axis == 1 ? row : 0);
             const int iz = a.axis == 2 ? row : 0;
@@ -71,12 +81,17 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     }
     fft_line<L, DIR>(v, t, a.tw, ex);
     if (valid) {
+        if (a.pushOn) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
+            for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+        }
     }
 }
 
-template <int L, int KIND>
+template <int L, int KIND, int SIG>
 __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB)
 axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
     using P = FftPlan<L>;
@@ -125,6 +140,33 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
         const long long off0 = axis_off(a.aout, b, t, col);
         const float2* sp = ks.src[0] + off0;
         float2* dp = ks.dst[0] + off0;
+        if constexpr (SIG >= 0) {
+            // exponent pattern known at compile time: short straight-line body, fully unrolled, loads batched by 8
+            const double tp[3] = {ks.sq2.tpre[0], ks.sq2.tpre[1], ks.sq2.tpre[2]};
+            const double ip[4] = {ks.sq2.ipre[0], ks.sq2.ipre[1], ks.sq2.ipre[2], ks.sq2.ipre[3]};
+            const bool termFused = ks.sq2.termFused != 0;
+            const float dt = ks.dt;
+            constexpr int CH = E < 8 ? E : 8;
+#pragma unroll
+            for (int e0 = 0; e0 < E; e0 += CH) {
+                float2 self[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) self[j] = valid ? __ldcg(sp + (e0 + j) * rowStride) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int e = e0 + j;
+                    const int row = t + T * e;
+                    const float qr = wavenumber(row, sRow, stepRow);
+                    const float qr2 = CUPSS_FMUL(qr, qr);
+                    const float q2 = CUPSS_FADD(CUPSS_FADD(qx2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
+                    float2 val = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2, v[e], self[j]);
+                    if (fixSelf && ((row == 0) || (2 * row == sRow))) val.y = 0.0f;
+                    if (valid) dp[e * rowStride] = val;
+                    const int nr = row > sRow / 2 ? sRow - row : row;
+                    v[e] = (keepFix && nr <= cutRow) ? val : make_float2(0.0f, 0.0f);
+                }
+            }
+        } else {
         constexpr int CH = E < 4 ? E : 4;
         int row0 = t;
 #pragma unroll 1
@@ -157,6 +199,7 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
             sp += CH * rowStride;
             dp += CH * rowStride;
         }
+        }
     } else {
         const unsigned int step = ks.stepCounter ? *ks.stepCounter : 0u;
 #pragma unroll
@@ -175,11 +218,20 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
     }
 
     if (ks.hasInv) {
+        if (a.pruneOn) {   // CTA-uniform: every mode of this tile is masked out -> nothing to transform or store
+            const int nyT = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
+            if (ct * C > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
+        }
         if (ks.hasFwd && P::R1 > 1) __syncthreads();   // exchange buffer still being read by the forward transform
         fft_line<L, +1>(v, t, a.tw, ex);
         if (valid) {
+            if (a.pushOn) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
+                for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+            }
         }
     }
 }
@@ -234,16 +286,32 @@ static cudaError_t launch_kstage_L(const AxisArgs& a, const KStageD& ks, cudaStr
     static bool attr = false;
     if (!attr) {
         if (AxisCfg<L>::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_GENERIC, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
             if (e != cudaSuccess) return e;
+            if constexpr (L >= 64) {
+                e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+                if (e != cudaSuccess) return e;
+            }
         }
         attr = true;
     }
     const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
-    if (ks.fastKind == KS_SCALAR_Q2) axis_kstage_kernel<L, KS_SCALAR_Q2><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
-    else axis_kstage_kernel<L, KS_GENERIC><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+    if (ks.fastKind == KS_SCALAR_Q2) {
+        const int sig = sq2_signature(ks.sq2);
+        if (L >= 64 && sig == SQ2_SIG_CAHN_HILLIARD) {
+            if constexpr (L >= 64) axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+        } else if (L >= 64 && sig == SQ2_SIG_DIFFUSION) {
+            if constexpr (L >= 64) axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+        } else {
+            axis_kstage_kernel<L, KS_SCALAR_Q2, -1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+        }
+    } else {
+        axis_kstage_kernel<L, KS_GENERIC, -1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+    }
     return cudaGetLastError();
 }
 

@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(256) xpass_kernel(const __grid_constant__ XArg
             for (int e = 0; e < E; ++e) {
                 const int idx = t + T * e;
                 const int k = idx <= SX / 2 ? idx : SX - idx;
-                float2 A = hasA ? __ldg(pa + k) : make_float2(0.0f, 0.0f);
-                float2 B = hasB ? __ldg(pb + k) : make_float2(0.0f, 0.0f);
+                const bool live = k <= a.kmax[g];
+                float2 A = (hasA && live) ? __ldg(pa + k) : make_float2(0.0f, 0.0f);
+                float2 B = (hasB && live) ? __ldg(pb + k) : make_float2(0.0f, 0.0f);
                 if (k == 0 || 2 * k == SX) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of self-conjugate bins
                 if (idx > SX / 2) { A.y = -A.y; B.y = -B.y; }
                 v[e] = make_float2(A.x - B.y, A.y + B.x);
@@ -90,16 +91,20 @@ __global__ void __launch_bounds__(256) xpass_kernel(const __grid_constant__ XArg
                 v[e].y = hasB ? __ldg(a.realIn + lineB * SX + x) : 0.0f;
             }
         } else if (FAST) {
-            // one input, one output: products of powers of the single field, straight from registers
+            // one input, one output, at most two monomials c*r^p with p <= 4: branch-free, straight from registers.
+            // r^p is the left-to-right product ((r*r)*r)*r of computeProduct (src/term.cpp:85-92).
+            const float c0 = a.mono[0].coef, c1 = a.nMono > 1 ? a.mono[1].coef : 0.0f;
+            const int p0 = a.mono[0].nfac, p1 = a.nMono > 1 ? a.mono[1].nfac : 0;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const float2 r = v[e];
-                float2 acc = make_float2(0.0f, 0.0f);
-                for (int m = 0; m < a.nMono; ++m) {
-                    float px = a.mono[m].coef, py = px;
-                    for (int f = 0; f < a.mono[m].nfac; ++f) { px *= r.x; py *= r.y; }
-                    acc.x += px; acc.y += py;
-                }
+                const float2 r2 = make_float2(r.x * r.x, r.y * r.y);
+                const float2 r3 = make_float2(r2.x * r.x, r2.y * r.y);
+                const float2 r4 = make_float2(r3.x * r.x, r3.y * r.y);
+#define CUPSS_RP(p, c) ((p) == 0 ? 1.0f : ((p) == 1 ? r.c : ((p) == 2 ? r2.c : ((p) == 3 ? r3.c : r4.c))))
+                float2 acc = make_float2(c0 * CUPSS_RP(p0, x), c0 * CUPSS_RP(p0, y));
+                if (a.nMono > 1) { acc.x += c1 * CUPSS_RP(p1, x); acc.y += c1 * CUPSS_RP(p1, y); }
+#undef CUPSS_RP
                 v[e] = acc;
             }
         } else {
@@ -178,7 +183,9 @@ static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
     } else {
         if (mode == X_C2R_ONLY) return launch_x<SX, X_C2R_ONLY, true>(a, st);
         if (mode == X_R2C_ONLY) return launch_x<SX, X_R2C_ONLY, true>(a, st);
-        if (a.nIn == 1 && a.nOut == 1) return launch_x<SX, X_HOT, true>(a, st);
+        bool fast = a.nIn == 1 && a.nOut == 1 && a.nMono >= 1 && a.nMono <= 2;
+        for (int m = 0; m < a.nMono && fast; ++m) fast = a.mono[m].nfac <= 4;
+        if (fast) return launch_x<SX, X_HOT, true>(a, st);
         return launch_x<SX, X_HOT, false>(a, st);
     }
 }
