@@ -185,3 +185,38 @@ def test_bench_reference_arm_rank1_is_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+REF_EXAMPLES = "/root/reference/examples"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference sources are only present in the build container")
+def test_reference_examples_compile_unchanged(built, tmp_path):
+    """Drop-in check at the source level: every example of the reference compiles and links, unedited,
+    against inc/cupss.h + lib/libcupss.so.  The sources are symlinked from where they lie (never copied into the repo);
+    the tree mirrors the reference's so that the examples' relative includes ("../../inc/cupss.h") resolve to OUR headers."""
+    from cupss_b200 import capi
+    (tmp_path / "examples").mkdir()
+    os.symlink(os.path.join(ROOT, "inc"), tmp_path / "inc")
+    srcs = []
+    for d in sorted(os.listdir(REF_EXAMPLES)):
+        full = os.path.join(REF_EXAMPLES, d)
+        if not os.path.isdir(full):
+            continue
+        (tmp_path / "examples" / d).mkdir()
+        for f in sorted(os.listdir(full)):
+            if f.endswith((".cpp", ".cu")):
+                os.symlink(os.path.join(full, f), tmp_path / "examples" / d / f)
+                srcs.append(str(tmp_path / "examples" / d / f))
+    assert len(srcs) >= 10
+    libdir, engdir = os.path.dirname(capi.PRODUCT_LIB), os.path.dirname(capi.ENGINE_LIB)
+    for s in srcs:
+        out = s + ".bin"
+        if s.endswith(".cu"):   # example 07: user kernels + callbacks, built with nvcc as its README says
+            cmd = ["nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-I", str(tmp_path / "inc"), s,
+                   "-L", libdir, "-lcupss", "-L", engdir, "-lcupss_b200", "-o", out]
+        else:
+            cmd = ["g++", "-std=c++17", "-O1", "-w", "-I", str(tmp_path / "inc"), "-I", "/usr/local/cuda/include", s,
+                   "-L", libdir, "-lcupss", "-L", engdir, "-lcupss_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-o", out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, (s, r.stderr[-2000:])
