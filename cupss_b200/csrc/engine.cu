@@ -174,11 +174,8 @@ struct cupss_b200_plan {
     int get_twiddle(int L, const float2** out) {
         auto it = twiddles.find(L);
         if (it != twiddles.end()) { *out = it->second; return CUPSS_B200_OK; }
-        std::vector<float2> h(L);
-        for (int k = 0; k < L; ++k) {
-            const double a = -2.0 * kPi * (double)k / (double)L;
-            h[k] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
+        std::vector<float2> h(L > 0 ? L : 1, make_float2(1.0f, 0.0f));
+        if (host_level_twiddles(L, h.data()) <= 0) return fail(CUPSS_B200_ERR_ARG, "unsupported transform length %d", L);
         float2* d = nullptr;
         CK(cudaMalloc(&d, sizeof(float2) * L));
         CK(cudaMemcpyAsync(d, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice, stream));
@@ -889,6 +886,7 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     p->ncol = sx / 2 + 1;
     p->pitch = (p->ncol + 15) / 16 * 16;
     p->specElems = (size_t)p->pitch * sy * sz;
+    if (p->specElems >= (1ull << 31)) { delete p; return fail(CUPSS_B200_ERR_ARG, "grid %dx%dx%d: the kernels index one array with 32 bits (< 2^31 complex elements)", sx, sy, sz); }
     const char* ng = getenv("CUPSS_B200_NO_GRAPH");
     p->useGraph = !(ng && ng[0] == '1');
     const char* np_ = getenv("CUPSS_B200_NO_PRUNE");

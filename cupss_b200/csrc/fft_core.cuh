@@ -1,18 +1,32 @@
-// fft_core.cuh -- register/shared-memory FFT building blocks for the sm_100a step kernels.
+// fft_core.cuh -- FFT building blocks of the sm_100a step kernels.
 //
 // Replaces the cuFFT C2C executions on the reference's hot path
 // (/root/reference/src/field.cpp:247-273 toReal/toComp, src/term.cpp:48-64 term::toComp).
 //
-// Every transform in this engine is a Stockham autosort FFT over a power-of-two line of L
-// points, executed by T = L/E threads that each own E points in registers ("canonical"
-// ownership: thread t holds points t + T*e, e = 0..E-1).  A pass of radix R does E/R
-// register butterflies per thread; between passes the line goes once through shared memory.
-// With E = 32 a 512-point line needs two passes (radix 32 then 16) and therefore ONE
-// shared-memory exchange -- the shared-memory crossbar (128 B/clk/SM), not HBM, is the
-// scarce resource for these kernels on B200, see DESIGN.md.
+// Every transform is an IN-PLACE mixed-radix FFT over a power-of-two line of L points that lives in
+// shared memory between passes ("levels").  With radices R1..Rn (L = R1*...*Rn) level l works on
+// independent blocks of N_l = L/(R1..R_{l-1}) points; one "virtual thread" v owns the R_l points
+//      row(q) = blk*N_l + j + M_l*q,   M_l = N_l/R_l,  blk = v / M_l,  j = v % M_l,  q = 0..R_l-1
+// reads them, does one radix-R_l butterfly in registers and writes the SAME positions back, so there
+// is no ping-pong buffer and no hazard inside a level (one __syncthreads between levels).
+//   decimation in frequency (DIF), levels 1..n : butterfly, then twiddle w_{N_l}^{j q}
+//              natural order in -> digit-reversed order out
+//   decimation in time (DIT),      levels n..1 : twiddle w_{N_l}^{j q}, then butterfly
+//              digit-reversed order in -> natural order out
+// for either sign of the exponent.  The strided-axis kernels run forward = DIF, inverse = DIT; the x pass
+// runs inverse = DIF, forward = DIT (its real-space stage sits in the middle and is pointwise).
+// Position p = q1*(L/R1) + q2*(L/(R1 R2)) + ... + qn holds frequency k = q1 + R1 q2 + R1 R2 q3 + ...
+// The permutation is free where it matters: the strided-axis kernels move whole 128-byte row segments
+// between global and shared memory, so a permuted ROW order costs nothing, and the k-space stage /
+// the real-space products are pointwise and do not care about the order at all.
+// A real thread loops over several virtual threads per level (rolled loop): few registers, a small
+// instruction footprint (the unrolled register-resident design this replaces overflowed the
+// instruction cache: 24 % "no instruction" stalls in profiles/r01a) and high occupancy.
+// Complex add/sub use the packed FP32 instructions of sm_100 (FADD2 / FFMA2): one issue slot per
+// complex operation -- these kernels are bound by issue slots and HBM, not by FP32 throughput.
 //
-// Everything here is __host__ __device__ so tests/host_fft_check.cu can run the very same
-// index arithmetic and butterflies on the CPU (there is no GPU in the build container).
+// Everything is __host__ __device__: tests/host/fft_core_check.cu runs the very same level arithmetic
+// on the CPU (there is no GPU in the build container).
 #pragma once
 #include <cuda_runtime.h>
 #include <utility>
@@ -22,13 +36,37 @@
 namespace cupss {
 
 // ---------------------------------------------------------------- complex helpers
-CUPSS_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-CUPSS_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 CUPSS_HD float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.y, b.x, a.x * b.y));
 }
+CUPSS_HD float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.y, b.y, a.x * b.x), fmaf(a.y, b.x, -(a.x * b.y)));
+}
 CUPSS_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 CUPSS_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// packed FP32x2 (one instruction per complex add / sub / scaled add on sm_100)
+CUPSS_HD float2 cadd(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+CUPSS_HD float2 csub(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);   // exact product, one rounding: == a - b
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+CUPSS_HD float2 cfma_s(float2 u, float s, float2 c) {   // u*s + c, componentwise
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(u, make_float2(s, s), c);
+#else
+    return make_float2(fmaf(u.x, s, c.x), fmaf(u.y, s, c.y));
+#endif
+}
 
 // ---------------------------------------------------------------- constexpr trig (compile-time twiddles)
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -44,41 +82,41 @@ __host__ __device__ constexpr double cx_cos(double x) {
     return sum;
 }
 
-// v * exp(DIR * 2*pi*i * K / N), K and N compile-time.  DIR = -1 forward, +1 inverse.
-template <int K, int N, int DIR>
-CUPSS_HD float2 twiddle_mul(float2 v) {
-    constexpr int k = ((K % N) + N) % N;
-    if constexpr (k == 0) {
-        return v;
-    } else if constexpr (2 * k == N) {
-        return make_float2(-v.x, -v.y);
-    } else if constexpr (4 * k == N) {          // * (DIR * i)
-        return DIR > 0 ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
-    } else if constexpr (4 * k == 3 * N) {      // * (-DIR * i)
-        return DIR > 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
-    } else if constexpr (8 * k == N) {          // (1 + DIR*i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return DIR > 0 ? make_float2((v.x - v.y) * h, (v.x + v.y) * h)
-                       : make_float2((v.x + v.y) * h, (v.y - v.x) * h);
-    } else if constexpr (8 * k == 3 * N) {      // (-1 + DIR*i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return DIR > 0 ? make_float2((-v.x - v.y) * h, (v.x - v.y) * h)
-                       : make_float2((v.y - v.x) * h, (-v.x - v.y) * h);
-    } else {
-        constexpr float c = (float)cx_cos(2.0 * kPi * k / N);
-        constexpr float s = (float)(DIR * cx_sin(2.0 * kPi * k / N));
-        return make_float2(fmaf(-v.y, s, v.x * c), fmaf(v.x, s, v.y * c));
-    }
-}
-
 // ---------------------------------------------------------------- in-register DFT of N points, natural order in/out
+// Recursive even/odd split; the combine step x[K] = e[K] + w^K o[K], x[K+N/2] = e[K] - w^K o[K]
+// (w = exp(DIR*2*pi*i/N)) folds the trivial twiddles into the adds.
 template <int N, int DIR>
 struct Dft {
     template <int K>
     static CUPSS_HD void comb1(float2 (&x)[N], const float2 (&e)[N / 2], const float2 (&o)[N / 2]) {
-        float2 t = twiddle_mul<K, N, DIR>(o[K]);
-        x[K] = cadd(e[K], t);
-        x[K + N / 2] = csub(e[K], t);
+        constexpr float h = 0.70710678118654752440f;
+        const float2 E = e[K], O = o[K];
+        if constexpr (K == 0) {
+            x[K] = cadd(E, O);
+            x[K + N / 2] = csub(E, O);
+        } else if constexpr (4 * K == N) {          // w^K = DIR*i
+            if constexpr (DIR > 0) {
+                x[K] = make_float2(E.x - O.y, E.y + O.x);
+                x[K + N / 2] = make_float2(E.x + O.y, E.y - O.x);
+            } else {
+                x[K] = make_float2(E.x + O.y, E.y - O.x);
+                x[K + N / 2] = make_float2(E.x - O.y, E.y + O.x);
+            }
+        } else if constexpr (8 * K == N) {          // w^K = (1 + DIR*i)/sqrt2
+            const float2 u = DIR > 0 ? make_float2(O.x - O.y, O.x + O.y) : make_float2(O.x + O.y, O.y - O.x);
+            x[K] = cfma_s(u, h, E);
+            x[K + N / 2] = cfma_s(u, -h, E);
+        } else if constexpr (8 * K == 3 * N) {      // w^K = (-1 + DIR*i)/sqrt2
+            const float2 u = DIR > 0 ? make_float2(O.x + O.y, O.y - O.x) : make_float2(O.x - O.y, O.x + O.y);
+            x[K] = cfma_s(u, -h, E);
+            x[K + N / 2] = cfma_s(u, h, E);
+        } else {
+            constexpr float c = (float)cx_cos(2.0 * kPi * K / N);
+            constexpr float s = (float)(DIR * cx_sin(2.0 * kPi * K / N));
+            const float2 t = make_float2(fmaf(-O.y, s, O.x * c), fmaf(O.x, s, O.y * c));
+            x[K] = cadd(E, t);
+            x[K + N / 2] = csub(E, t);
+        }
     }
     template <int... K>
     static CUPSS_HD void combine(float2 (&x)[N], const float2 (&e)[N / 2], const float2 (&o)[N / 2],
@@ -99,106 +137,154 @@ struct Dft<1, DIR> { static CUPSS_HD void run(float2 (&)[1]) {} };
 template <int DIR>
 struct Dft<2, DIR> {
     static CUPSS_HD void run(float2 (&x)[2]) {
-        float2 a = x[0], b = x[1];
+        const float2 a = x[0], b = x[1];
         x[0] = cadd(a, b); x[1] = csub(a, b);
     }
 };
-template <int DIR>
-struct Dft<4, DIR> {
-    static CUPSS_HD void run(float2 (&x)[4]) {
-        float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
-        float2 t2 = cadd(x[1], x[3]), t3 = twiddle_mul<1, 4, DIR>(csub(x[1], x[3]));
-        x[0] = cadd(t0, t2); x[1] = cadd(t1, t3); x[2] = csub(t0, t2); x[3] = csub(t1, t3);
-    }
+
+// ---------------------------------------------------------------- level plan: L -> radices
+template <int L> struct FftLevels;
+#define CUPSS_LEVELS(L_, N_, A_, B_, C_, D_)                                              \
+    template <> struct FftLevels<L_> {                                                    \
+        static constexpr int n = N_;                                                      \
+        __host__ __device__ static constexpr int rad(int l) { return l == 0 ? A_ : (l == 1 ? B_ : (l == 2 ? C_ : D_)); } \
+        __host__ __device__ static constexpr int min_rad() {                                                          \
+            int m = A_;                                                                                               \
+            if (N_ > 1 && B_ < m) m = B_;                                                                             \
+            if (N_ > 2 && C_ < m) m = C_;                                                                             \
+            if (N_ > 3 && D_ < m) m = D_;                                                                             \
+            return m;                                                                                                 \
+        }                                                                                                             \
+    };
+CUPSS_LEVELS(1, 1, 1, 1, 1, 1)
+CUPSS_LEVELS(2, 1, 2, 1, 1, 1)
+CUPSS_LEVELS(4, 1, 4, 1, 1, 1)
+CUPSS_LEVELS(8, 1, 8, 1, 1, 1)
+CUPSS_LEVELS(16, 1, 16, 1, 1, 1)
+CUPSS_LEVELS(32, 2, 4, 8, 1, 1)
+CUPSS_LEVELS(64, 2, 8, 8, 1, 1)
+CUPSS_LEVELS(128, 2, 16, 8, 1, 1)
+CUPSS_LEVELS(256, 2, 16, 16, 1, 1)
+CUPSS_LEVELS(512, 3, 8, 8, 8, 1)
+CUPSS_LEVELS(1024, 3, 16, 8, 8, 1)
+CUPSS_LEVELS(2048, 3, 16, 16, 8, 1)
+CUPSS_LEVELS(4096, 3, 16, 16, 16, 1)
+CUPSS_LEVELS(8192, 4, 16, 8, 8, 8)
+#undef CUPSS_LEVELS
+
+template <int L, int LV> struct LevelGeom {
+    static constexpr int R = FftLevels<L>::rad(LV);
+    static constexpr int NB = LV == 0 ? 1 : (LV == 1 ? FftLevels<L>::rad(0) : (LV == 2 ? FftLevels<L>::rad(0) * FftLevels<L>::rad(1)
+                                                                                      : FftLevels<L>::rad(0) * FftLevels<L>::rad(1) * FftLevels<L>::rad(2)));
+    static constexpr int N = L / NB;     // block length at this level
+    static constexpr int M = N / R;      // stride between the R points of one butterfly
+    static constexpr int NV = L / R;     // virtual threads of this level
+    static constexpr int TWS = L / N;    // twiddle w_N^(j q) = exp(-2*pi*i * TWS*j*q / L)
+    // Level twiddle table (built on the host, level_twiddles()): entry TWOFF + (q-1)*M + j holds w_N^(j q),
+    // q = 1..R-1, j = 0..M-1 -- consecutive j are consecutive words, so a warp's loads are conflict-free and every
+    // address is "j + compile-time offset".  Levels with M == 1 have no twiddles.
+    static constexpr int TWCNT = M > 1 ? (R - 1) * M : 0;
+    static constexpr int TWOFF = LV == 0 ? 0 : LevelGeom<L, (LV > 0 ? LV - 1 : 0)>::TWOFF + LevelGeom<L, (LV > 0 ? LV - 1 : 0)>::TWCNT;
+};
+template <int L> struct TwTable {
+    static constexpr int LEN_ = LevelGeom<L, 3>::TWOFF + LevelGeom<L, 3>::TWCNT;   // levels beyond n have R = 1: TWCNT = 0
+    static constexpr int LEN = LEN_ > 0 ? LEN_ : 1;
 };
 
-// ---------------------------------------------------------------- one Stockham pass on canonical registers
-// Line of L points, E per thread (T = L/E threads), radix R, NS = product of earlier radices.
-// Register e = m + r*(E/R) is input r of butterfly j = t + T*m (point j + r*L/R); after the
-// call it holds output r of that butterfly, which belongs at point stockham_out_index().
-// `tw` is the forward table exp(-2*pi*i*k/L), k = 0..L-1 (conjugated on the fly for DIR=+1).
-template <int L, int E, int R, int NS, int DIR>
-CUPSS_HD void stockham_pass(float2 (&v)[E], int t, const float2* __restrict__ tw) {
-    constexpr int T = L / E, M = E / R;
-    static_assert(E % R == 0 && L % E == 0, "bad FFT factorisation");
+// Frequency held at position p after the forward (digit-reversed) transform; its own inverse for symmetric
+// radix lists, and in general the map the inverse transform expects on input.
+template <int L>
+CUPSS_HD unsigned freq_of_pos(unsigned p) {
+    using F = FftLevels<L>;
+    unsigned k = 0, w = 1, rem = p, n = L;
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-        float2 a[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) a[r] = v[m + r * M];
-        if constexpr (NS > 1) {
-            const int k = (t + T * m) & (NS - 1);
-            constexpr int step = L / (NS * R);
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
-#ifdef __CUDA_ARCH__
-                float2 w = __ldg(tw + r * k * step);
-#else
-                float2 w = tw[r * k * step];
-#endif
-                if (DIR > 0) w.y = -w.y;
-                a[r] = cmul(a[r], w);
-            }
+    for (int l = 0; l < F::n; ++l) {
+        n /= F::rad(l);
+        const unsigned q = rem / n;
+        rem -= q * n;
+        k += q * w;
+        w *= F::rad(l);
+    }
+    return k;
+}
+
+// Host: fill the level twiddle table of L (TwTable<L>::LEN entries).
+template <int L, int LV>
+inline void fill_level_twiddles(float2* out) {
+    if constexpr (LV < FftLevels<L>::n) {
+        using G = LevelGeom<L, LV>;
+        if constexpr (G::M > 1) {
+            for (int q = 1; q < G::R; ++q)
+                for (int j = 0; j < G::M; ++j) {
+                    const long long k = ((long long)G::TWS * j * q) % L;
+                    const double a = -2.0 * kPi * (double)k / (double)L;
+                    out[G::TWOFF + (q - 1) * G::M + j] = make_float2((float)__builtin_cos(a), (float)__builtin_sin(a));
+                }
         }
-        Dft<R, DIR>::run(a);
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[m + r * M] = a[r];
+        fill_level_twiddles<L, LV + 1>(out);
     }
 }
 
-// Point index where register e (of thread t) must be stored after a radix-R pass with stride NS.
-template <int L, int E, int R, int NS>
-CUPSS_HD int stockham_out_index(int t, int e) {
-    constexpr int T = L / E, M = E / R;
-    const int m = e % M, r = e / M;
-    const int j = t + T * m;
-    return (j / NS) * NS * R + (j & (NS - 1)) + r * NS;
+// Position that holds frequency k after the forward transform (inverse map of freq_of_pos).
+template <int L>
+CUPSS_HD unsigned pos_of_freq(unsigned k) {
+    using F = FftLevels<L>;
+    unsigned p = 0, n = L, rem = k;
+#pragma unroll
+    for (int l = 0; l < F::n; ++l) {
+        const unsigned r = F::rad(l);
+        n /= r;
+        p += (rem % r) * n;
+        rem /= r;
+    }
+    return p;
 }
 
-// ---------------------------------------------------------------- plan selection: L -> (E, R0, R1, R2)
-template <int L> struct FftPlan;
-#define CUPSS_FFTPLAN(L_, E_, R0_, R1_, R2_) \
-    template <> struct FftPlan<L_> { static constexpr int E = E_, R0 = R0_, R1 = R1_, R2 = R2_, T = L_ / E_; };
-CUPSS_FFTPLAN(1, 1, 1, 1, 1)
-CUPSS_FFTPLAN(2, 2, 2, 1, 1)
-CUPSS_FFTPLAN(4, 4, 4, 1, 1)
-CUPSS_FFTPLAN(8, 8, 8, 1, 1)
-CUPSS_FFTPLAN(16, 16, 16, 1, 1)
-CUPSS_FFTPLAN(32, 32, 32, 1, 1)
-CUPSS_FFTPLAN(64, 16, 8, 8, 1)
-CUPSS_FFTPLAN(128, 16, 16, 8, 1)
-CUPSS_FFTPLAN(256, 16, 16, 16, 1)
-CUPSS_FFTPLAN(512, 32, 32, 16, 1)
-CUPSS_FFTPLAN(1024, 32, 32, 32, 1)
-CUPSS_FFTPLAN(2048, 32, 16, 16, 8)
-CUPSS_FFTPLAN(4096, 32, 16, 16, 16)
-CUPSS_FFTPLAN(8192, 32, 32, 16, 16)
-#undef CUPSS_FFTPLAN
+// One level on one virtual thread; `x` holds the R points in butterfly order q = 0..R-1.
+//   SIGN: sign of the exponent (-1 forward, +1 inverse).
+//   DIF : true  -> butterfly, then twiddle exp(SIGN*2*pi*i*j*q/N)   (natural order in, digit-reversed out)
+//         false -> twiddle, then butterfly                           (digit-reversed in, natural order out)
+// `tw` is the level twiddle table of L (forward sign; conjugated on the fly for SIGN > 0).
+template <int L, int LV, int SIGN, bool DIF>
+CUPSS_HD void level_butterfly(float2 (&x)[LevelGeom<L, LV>::R], unsigned j, const float2* __restrict__ tw) {
+    using G = LevelGeom<L, LV>;
+    constexpr int R = G::R;
+    if constexpr (!DIF && G::M > 1) {
+        const float2* t = tw + G::TWOFF + j;
+#pragma unroll
+        for (int q = 1; q < R; ++q) x[q] = SIGN > 0 ? cmul_conj(x[q], t[(q - 1) * G::M]) : cmul(x[q], t[(q - 1) * G::M]);
+    }
+    Dft<R, SIGN>::run(x);
+    if constexpr (DIF && G::M > 1) {
+        const float2* t = tw + G::TWOFF + j;
+#pragma unroll
+        for (int q = 1; q < R; ++q) x[q] = SIGN > 0 ? cmul_conj(x[q], t[(q - 1) * G::M]) : cmul(x[q], t[(q - 1) * G::M]);
+    }
+}
 
-// Full line FFT on canonical registers.  `Ex` provides the shared-memory exchange:
-//   ex.st(point, value), ex.ld(point), ex.sync().
-// On entry the exchange buffer must be free; on exit other threads may still be reading it,
-// so callers sync before re-using it.  Result is canonical (thread t holds points t + T*e).
-template <int L, int DIR, class Ex>
-CUPSS_HD void fft_line(float2 (&v)[FftPlan<L>::E], int t, const float2* __restrict__ tw, Ex& ex) {
-    using P = FftPlan<L>;
-    constexpr int E = P::E, T = P::T, R0 = P::R0, R1 = P::R1, R2 = P::R2;
-    stockham_pass<L, E, R0, 1, DIR>(v, t, tw);
-    if constexpr (R1 > 1) {
+// Same for two independent lines (the two columns / two jobs a thread carries): every twiddle is loaded once.
+template <int L, int LV, int SIGN, bool DIF>
+CUPSS_HD void level_butterfly2(float2 (&x)[LevelGeom<L, LV>::R], float2 (&y)[LevelGeom<L, LV>::R], unsigned j, const float2* __restrict__ tw) {
+    using G = LevelGeom<L, LV>;
+    constexpr int R = G::R;
+    if constexpr (!DIF && G::M > 1) {
+        const float2* t = tw + G::TWOFF + j;
 #pragma unroll
-        for (int e = 0; e < E; ++e) ex.st(stockham_out_index<L, E, R0, 1>(t, e), v[e]);
-        ex.sync();
+        for (int q = 1; q < R; ++q) {
+            const float2 w = t[(q - 1) * G::M];
+            x[q] = SIGN > 0 ? cmul_conj(x[q], w) : cmul(x[q], w);
+            y[q] = SIGN > 0 ? cmul_conj(y[q], w) : cmul(y[q], w);
+        }
+    }
+    Dft<R, SIGN>::run(x);
+    Dft<R, SIGN>::run(y);
+    if constexpr (DIF && G::M > 1) {
+        const float2* t = tw + G::TWOFF + j;
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = ex.ld(t + T * e);
-        stockham_pass<L, E, R1, R0, DIR>(v, t, tw);
-        if constexpr (R2 > 1) {
-            ex.sync();
-#pragma unroll
-            for (int e = 0; e < E; ++e) ex.st(stockham_out_index<L, E, R1, R0>(t, e), v[e]);
-            ex.sync();
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = ex.ld(t + T * e);
-            stockham_pass<L, E, R2, R0 * R1, DIR>(v, t, tw);
+        for (int q = 1; q < R; ++q) {
+            const float2 w = t[(q - 1) * G::M];
+            x[q] = SIGN > 0 ? cmul_conj(x[q], w) : cmul(x[q], w);
+            y[q] = SIGN > 0 ? cmul_conj(y[q], w) : cmul(y[q], w);
         }
     }
 }

@@ -87,6 +87,8 @@ cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st);
 cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
+// Level twiddle table of an L-point transform (fft_core.cuh); returns the number of entries written (<= L), 0 if unsupported.
+int host_level_twiddles(int L, float2* out);
 bool fft_size_supported(int n);
 
 }  // namespace cupss

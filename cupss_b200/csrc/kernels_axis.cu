@@ -1,92 +1,146 @@
 // kernels_axis.cu -- strided-axis FFT passes (y and z) of the half-spectrum, plain and fused.
 //
-// A CTA owns a tile [L rows] x [C columns] of one k-space array: the L points of C neighbouring
-// kx columns along the transformed axis.  Lanes map to columns, so every global access of a
-// half-warp is one contiguous, 128-byte-aligned row segment (C = 16 float2) and every
-// shared-memory access is conflict-free.  Thread (t, c) owns points t + T*e of column c.
+// A CTA owns a tile [L rows] x [C columns] of one k-space array: the L points of C neighbouring kx columns
+// along the transformed axis, held in shared memory as float4 = two neighbouring columns, so every global
+// and shared access is a 128-bit access and a quarter-warp moves one contiguous, 128-byte-aligned row
+// segment (C = 16 float2).  The transform runs in place on the tile, level by level (fft_core.cuh); rows are
+// permuted for free on the way in / out because a row is a whole coalesced segment.
 //
 //   axis_plain_kernel  : load -> FFT -> store                      (y passes of a 3-D transform;
 //                        optional dealias mask on load for extra inverse transforms)
 //   axis_kstage_kernel : [load -> forward FFT] -> per-mode update of every field of the sweep
 //                        (kstage_point) -> [dealias -> inverse FFT -> store]
-// The second is the heart of the step: the last pass of the forward transform of the nonlinear
-// term, the semi-implicit Euler update, the dealiasing mask and the first pass of the next inverse
-// transform happen on data that never leaves the SM.
+// The second is the heart of the step: the last level of the forward transform of the nonlinear term, the
+// semi-implicit Euler update, the dealiasing mask and the first level of the next inverse transform happen
+// on the same registers; the data never leaves the SM between the two transforms.
 #include "kernels.h"
 
 namespace cupss {
 
-template <int C, int PADR>
-struct TileEx {
-    float2* buf;
-    int c;
-    __device__ __forceinline__ static int prow(int idx) { return PADR > 0 ? idx + idx / PADR : idx; }
-    __device__ __forceinline__ void st(int idx, float2 v) { buf[prow(idx) * C + c] = v; }
-    __device__ __forceinline__ float2 ld(int idx) const { return buf[prow(idx) * C + c]; }
-    __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-
 template <int L> struct AxisCfg {
     static constexpr int C = L <= 512 ? 16 : (L <= 2048 ? 8 : (L <= 4096 ? 4 : 2));
-    static constexpr int PADR = C < 16 ? FftPlan<L>::R0 : 0;
-    static constexpr int ROWS = PADR > 0 ? L + L / PADR + 1 : L;
-    static constexpr int THREADS = FftPlan<L>::T * C;
-    static constexpr int MINB = THREADS >= 512 ? 1 : 512 / THREADS;   // cap registers at 128/thread: >= 16 warps per SM
-    static constexpr size_t SMEM = FftPlan<L>::R1 > 1 ? (size_t)ROWS * C * sizeof(float2) : 0;
+    static constexpr int CP = C / 2;                                   // float4 column pairs
+    static constexpr int NVMAX = L / FftLevels<L>::min_rad();          // most virtual threads any level has
+    static constexpr size_t TILE = (size_t)L * CP * sizeof(float4);
+    static constexpr size_t SMEM = (FftLevels<L>::n > 1 ? TILE : 0) + (size_t)TwTable<L>::LEN * sizeof(float2);
+    static constexpr int WANT = CP * NVMAX;
+    static constexpr int TMAX = SMEM > 100 * 1024 ? 512 : 256;
+    static constexpr int THREADS = WANT < 32 ? 32 : (WANT > TMAX ? TMAX : WANT);
+    static constexpr int TV = THREADS / CP;
+    static constexpr int MINB = THREADS >= 512 ? 1 : (SMEM > 100 * 1024 ? 1 : (SMEM > 70 * 1024 ? 2 : 3));
 };
 
-__device__ __forceinline__ long long axis_off(const AxisAddr& a, int b, int row, int col) {
-    return (long long)b * a.bs + (long long)(row >> a.rpcShift) * a.cs + (long long)(row & a.rpcMask) * a.rs + col;
+// Element offset of (batch b, row, column col).  32-bit arithmetic: the engine refuses arrays of 2^31 elements or more.
+__device__ __forceinline__ unsigned axis_off(const AxisAddr& a, unsigned b, unsigned row, unsigned col) {
+    return b * (unsigned)a.bs + (row >> a.rpcShift) * (unsigned)a.cs + (row & (unsigned)a.rpcMask) * (unsigned)a.rs + col;
+}
+// Same with the row-independent part (b * bs + col) hoisted by the caller.
+__device__ __forceinline__ unsigned row_off(const AxisAddr& a, unsigned row) {
+    return (row >> a.rpcShift) * (unsigned)a.cs + (row & (unsigned)a.rpcMask) * (unsigned)a.rs;
 }
 
-// Destination of row `row` of batch b: local array, or the receive buffer of the peer that owns the row.
-__device__ __forceinline__ float2* axis_dst(const AxisArgs& a, int b, int row, int col) {
+// Destination of row `row`: local array, or the receive buffer of the peer that owns the row (fused slab exchange).
+// `lbase` = out + b*bs + col (local), `pbase` = pushBase + b*pushBs + col (element offset inside every peer's arena).
+__device__ __forceinline__ float2* axis_dst(const AxisArgs& a, float2* lbase, unsigned long long pbase, unsigned row) {
     if (a.pushOn)
-        return a.push[row >> a.pushShift] + a.pushBase + (long long)b * a.pushBs + (long long)(row & a.pushMask) * a.pushRs + col;
-    return a.out + axis_off(a.aout, b, row, col);
+        return a.push[row >> a.pushShift] + pbase + (unsigned long long)((row & (unsigned)a.pushMask)) * (unsigned long long)a.pushRs;
+    return lbase + row_off(a.aout, row);
 }
 
-template <int L, int DIR>
+__device__ __forceinline__ float4 ld4(const float2* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// One level over the tile: every real thread walks its virtual threads (v = tv, tv + TV, ...).
+//   ld(pos, frow) -> float4, st(pos, frow, value);  pos = position inside the tile, frow = frequency row that
+//   position holds in the digit-reversed order (only meaningful on the innermost level, M == 1).
+template <int L, int LV, int DIR, int TV, class LdF, class StF>
+__device__ __forceinline__ void tile_level(unsigned tv, const float2* __restrict__ twS, LdF ld, StF st) {
+    using G = LevelGeom<L, LV>;
+    constexpr unsigned R = G::R, M = G::M, N = G::N;
+#pragma unroll 1
+    for (unsigned v = tv; v < (unsigned)G::NV; v += TV) {
+        const unsigned blk = v / M, j = v % M;
+        const unsigned row0 = blk * N + j;
+        const unsigned f0 = M == 1 ? freq_of_pos<L>(v * R) : 0u;
+        float2 x0[R], x1[R];
+#pragma unroll
+        for (unsigned q = 0; q < R; ++q) {
+            const float4 t = ld(row0 + M * q, f0 + (L / R) * q);
+            x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
+        }
+        level_butterfly2<L, LV, DIR, (DIR < 0)>(x0, x1, j, twS);
+#pragma unroll
+        for (unsigned q = 0; q < R; ++q) st(row0 + M * q, f0 + (L / R) * q, make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y));
+    }
+}
+
+// MASK: apply the full dealias mask on load (extra inverse transforms of a sweep; AxisArgs::maskOn).
+template <int L, int DIR, bool MASK>
 __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_plain_kernel(const __grid_constant__ AxisArgs a) {
-    using P = FftPlan<L>;
-    constexpr int E = P::E, T = P::T, C = AxisCfg<L>::C;
-    extern __shared__ float2 smem[];
-    const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int ct = blockIdx.x % a.ncolTiles, b = blockIdx.x / a.ncolTiles;
-    const int col = ct * C + c;
-    const bool valid = col < a.ncol;
-    TileEx<C, AxisCfg<L>::PADR> ex{smem, c};
+    using Cfg = AxisCfg<L>;
+    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, n = FftLevels<L>::n;
+    extern __shared__ float4 smem4[];
+    float4* tile = smem4;
+    float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
+    const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
+    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles, b = blockIdx.x / (unsigned)a.ncolTiles;
+    const unsigned col = ct * C + 2 * cp;
+    const bool valid = col < (unsigned)a.ncol;
 
     if (a.pruneOn) {   // CTA-uniform: the whole tile is outside the dealias cut-off -> output stays zero
-        const int iyT = a.kyBase + b;
+        const int iyT = a.kyBase + (int)b;
         const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
-        if (ct * C > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
+        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
     }
+    for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
+    __syncthreads();
 
-    float2 v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int row = t + T * e;
-        bool keep = valid;
-        if (a.rowCut >= 0) {
-            const int nr = row > L / 2 ? L - row : row;
-            keep = keep && nr <= a.rowCut;
+    const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
+    float2* lbase = a.out + (b * (unsigned)a.aout.bs + col);
+    const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
+    // rows beyond rowCut (|n| > rowCut) are known zeros: not loaded.  rowCut < 0: off.
+    const unsigned keepLo = a.rowCut >= 0 ? (unsigned)a.rowCut : (unsigned)L, keepHi = a.rowCut >= 0 ? (unsigned)(L - a.rowCut) : 0u;
+
+    auto gload = [&](unsigned row) -> float4 {
+        if (!(valid && (row <= keepLo || row >= keepHi))) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 t = ld4(ibase + row_off(a.ain, row));
+        if constexpr (MASK) {
+            const int iy = a.axis == 2 ? a.kyBase + (int)b : (a.axis == 1 ? (int)row : 0);
+            const int iz = a.axis == 2 ? (int)row : 0;
+            if (!dealias_keep((int)col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.x = 0.0f; t.y = 0.0f; }
+            if (!dealias_keep((int)col + 1, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.z = 0.0f; t.w = 0.0f; }
         }
-        if (a.maskOn) {
-            const int iy = a.axis == 2 ? a.kyBase + b : (a.axis == 1 ? row : 0);
-            const int iz = a.axis == 2 ? row : 0;
-            keep = keep && dealias_keep(col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz);
-        }
-        v[e] = keep ? __ldg(a.in + axis_off(a.ain, b, row, col)) : make_float2(0.0f, 0.0f);
-    }
-    fft_line<L, DIR>(v, t, a.tw, ex);
-    if (valid) {
-        if (a.pushOn) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
+        return t;
+    };
+    auto gstore = [&](unsigned row, float4 v) {
+        if (valid) st4(axis_dst(a, lbase, pbase, row), v);
+    };
+    auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
+    auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
+
+    if constexpr (DIR < 0) {   // forward: natural rows in, frequency rows out
+        auto gld = [&](unsigned pos, unsigned) -> float4 { return gload(pos); };
+        auto gst = [&](unsigned, unsigned frow, float4 v) { gstore(frow, v); };
+        if constexpr (n == 1) {
+            tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
         } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
+            tile_level<L, 0, DIR, TV>(tv, twS, gld, sst);
+            __syncthreads();
+            if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
+            tile_level<L, n - 1, DIR, TV>(tv, twS, sld, gst);
+        }
+    } else {                   // inverse: frequency rows in, natural rows out
+        auto gld = [&](unsigned, unsigned frow) -> float4 { return gload(frow); };
+        auto gst = [&](unsigned pos, unsigned, float4 v) { gstore(pos, v); };
+        if constexpr (n == 1) {
+            tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
+        } else {
+            tile_level<L, n - 1, DIR, TV>(tv, twS, gld, sst);
+            __syncthreads();
+            if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
+            tile_level<L, 0, DIR, TV>(tv, twS, sld, gst);
         }
     }
 }
@@ -94,144 +148,170 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
 template <int L, int KIND, int SIG>
 __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB)
 axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
-    using P = FftPlan<L>;
-    constexpr int E = P::E, T = P::T, C = AxisCfg<L>::C;
-    extern __shared__ float2 smem[];
-    const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int ct = blockIdx.x % a.ncolTiles, b = blockIdx.x / a.ncolTiles;
-    const int col = ct * C + c;
-    const bool valid = col < a.ncol;
-    TileEx<C, AxisCfg<L>::PADR> ex{smem, c};
+    using Cfg = AxisCfg<L>;
+    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, n = FftLevels<L>::n;
+    constexpr int LAST = n - 1;
+    using G = LevelGeom<L, LAST>;
+    constexpr unsigned R = G::R;
+    extern __shared__ float4 smem4[];
+    float4* tile = smem4;
+    float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
+    const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
+    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles, b = blockIdx.x / (unsigned)a.ncolTiles;
+    const unsigned col = ct * C + 2 * cp;
+    const bool valid = col < (unsigned)a.ncol, valid1 = col + 1 < (unsigned)a.ncol;
 
-    float2 v[E];
-    if (ks.hasFwd) {
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-            v[e] = valid ? __ldg(a.in + axis_off(a.ain, b, t + T * e, col)) : make_float2(0.0f, 0.0f);
-        if (KIND == KS_SCALAR_Q2 && c == 0) {
-            // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
-#pragma unroll
-            for (int e = 0; e < E; ++e)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ks.src[0] + axis_off(a.aout, b, t + T * e, col)));
-        }
-        fft_line<L, -1>(v, t, a.tw, ex);
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = make_float2(0.0f, 0.0f);
+    // fixed (per thread) part of the mode index: columns = kx, and ky for a z pass
+    const int iyFix = a.axis == 2 ? a.kyBase + (int)b : 0;
+    bool doInv = ks.hasInv != 0;
+    if (doInv && a.pruneOn) {   // CTA-uniform: every mode of this tile is masked out -> nothing to transform or store
+        const int nyT = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
+        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) doInv = false;
     }
 
-    // fixed (per thread) part of the mode index: column = kx, and ky for a z pass
-    const int iyFix = a.axis == 2 ? a.kyBase + b : 0;
-    if (KIND == KS_SCALAR_Q2) {
-        // Lean path.  The point loop is ROLLED (CH points per trip) to keep the kernel inside the instruction
-        // cache; the register array is rotated by CH after every trip so that all indices stay static.
-        const OutD& od = ks.out[0];
-        const int sRow = a.axis == 2 ? ks.sz : (a.axis == 1 ? ks.sy : 1);
-        const float stepRow = a.axis == 2 ? ks.stepqz : ks.stepqy;
-        const int cutRow = a.axis == 2 ? od.cutz : od.cuty;
-        const float qx = wavenumber(col, ks.sx, ks.stepqx);
-        const float qyFix = wavenumber(iyFix, ks.sy, ks.stepqy);
-        const float qx2 = CUPSS_FMUL(qx, qx);
-        const float qyFix2 = CUPSS_FMUL(qyFix, qyFix);
-        const bool fixSelf = ((col == 0) || (2 * col == ks.sx)) && ((iyFix == 0) || (2 * iyFix == ks.sy));
-        const int nyFix = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
-        const bool keepFix = od.inv && col <= od.cutx && (a.axis != 2 || nyFix <= od.cuty);
-        const long long rowStride = (long long)T * a.aout.rs;          // natural layout: consecutive e are T rows apart
-        const long long off0 = axis_off(a.aout, b, t, col);
-        const float2* sp = ks.src[0] + off0;
-        float2* dp = ks.dst[0] + off0;
-        if constexpr (SIG >= 0) {
-            // exponent pattern known at compile time: short straight-line body, fully unrolled, loads batched by 8
+    // k-space arrays (sources, destinations) share the natural addressing of the pass output: b*bs + row*rs + col
+    const unsigned kbase = b * (unsigned)a.aout.bs + col;
+    const unsigned krs = (unsigned)a.aout.rs;
+    const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
+    float2* lbase = a.out + kbase;
+    const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
+
+    for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
+    if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
+        // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
+        const float2* p0 = ks.src[0] + (b * (unsigned)a.aout.bs + ct * C);
+        for (unsigned r = threadIdx.x; r < (unsigned)L; r += Cfg::THREADS)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + r * krs));
+    }
+    __syncthreads();
+
+    auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
+    auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
+
+    // ---- forward levels 0 .. n-2 (the last level is fused with the k stage below)
+    if (ks.hasFwd) {
+        if constexpr (n > 1) {
+            auto gld = [&](unsigned pos, unsigned) -> float4 {
+                return valid ? ld4(ibase + row_off(a.ain, pos)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            };
+            tile_level<L, 0, -1, TV>(tv, twS, gld, sst);
+            __syncthreads();
+            if constexpr (n >= 3) { tile_level<L, 1, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 4) { tile_level<L, 2, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
+        }
+    }
+
+    // ---- per-thread constants of the lean evaluator
+    const OutD& od0 = ks.out[0];
+    const int sRow = a.axis == 2 ? ks.sz : (a.axis == 1 ? ks.sy : 1);
+    const float stepRow = a.axis == 2 ? ks.stepqz : ks.stepqy;
+    const int cutRow = a.axis == 2 ? od0.cutz : od0.cuty;
+    const float qxa = wavenumber((int)col, ks.sx, ks.stepqx), qxb = wavenumber((int)col + 1, ks.sx, ks.stepqx);
+    const float qyFix = wavenumber(iyFix, ks.sy, ks.stepqy);
+    const float qxa2 = CUPSS_FMUL(qxa, qxa), qxb2 = CUPSS_FMUL(qxb, qxb);
+    const float qyFix2 = CUPSS_FMUL(qyFix, qyFix);
+    const bool fixY = (iyFix == 0) || (2 * iyFix == ks.sy);
+    const bool fixSelfA = ((col == 0) || (2 * (int)col == ks.sx)) && fixY;
+    const bool fixSelfB = (2 * ((int)col + 1) == ks.sx) && fixY;
+    const int nyFix = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
+    const bool keepY = od0.inv && (a.axis != 2 || nyFix <= od0.cuty);
+    const bool keepA = keepY && (int)col <= od0.cutx, keepB = keepY && (int)col + 1 <= od0.cutx;
+    const unsigned int step = (KIND == KS_GENERIC && ks.stepCounter) ? *ks.stepCounter : 0u;
+
+    // ---- fused level: last forward butterfly -> k stage -> first inverse butterfly
+#pragma unroll 1
+    for (unsigned v = tv; v < (unsigned)G::NV; v += TV) {
+        const unsigned f0 = freq_of_pos<L>(v * R);
+        float2 x0[R], x1[R];
+        if (ks.hasFwd) {
+#pragma unroll
+            for (unsigned q = 0; q < R; ++q) {
+                float4 t;
+                if constexpr (n > 1) t = tile[(v * R + q) * CP + cp];
+                else t = valid ? ld4(ibase + row_off(a.ain, v * R + q)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
+            }
+            level_butterfly2<L, LAST, -1, true>(x0, x1, 0, twS);
+        } else {
+#pragma unroll
+            for (unsigned q = 0; q < R; ++q) { x0[q] = make_float2(0.0f, 0.0f); x1[q] = make_float2(0.0f, 0.0f); }
+        }
+
+        if constexpr (KIND == KS_SCALAR_Q2) {
+            const unsigned rowStride = (L / R) * krs;
+            const unsigned off0 = kbase + f0 * krs;
+            const float2* sp = ks.src[0] + off0;
+            float2* dp = ks.dst[0] + off0;
+            float4 self[R];
+#pragma unroll
+            for (unsigned q = 0; q < R; ++q)
+                self[q] = valid ? __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             const double tp[3] = {ks.sq2.tpre[0], ks.sq2.tpre[1], ks.sq2.tpre[2]};
             const double ip[4] = {ks.sq2.ipre[0], ks.sq2.ipre[1], ks.sq2.ipre[2], ks.sq2.ipre[3]};
             const bool termFused = ks.sq2.termFused != 0;
             const float dt = ks.dt;
-            constexpr int CH = E < 8 ? E : 8;
 #pragma unroll
-            for (int e0 = 0; e0 < E; e0 += CH) {
-                float2 self[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) self[j] = valid ? __ldcg(sp + (e0 + j) * rowStride) : make_float2(0.0f, 0.0f);
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int e = e0 + j;
-                    const int row = t + T * e;
-                    const float qr = wavenumber(row, sRow, stepRow);
-                    const float qr2 = CUPSS_FMUL(qr, qr);
-                    const float q2 = CUPSS_FADD(CUPSS_FADD(qx2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
-                    float2 val = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2, v[e], self[j]);
-                    if (fixSelf && ((row == 0) || (2 * row == sRow))) val.y = 0.0f;
-                    if (valid) dp[e * rowStride] = val;
-                    const int nr = row > sRow / 2 ? sRow - row : row;
-                    v[e] = (keepFix && nr <= cutRow) ? val : make_float2(0.0f, 0.0f);
-                }
-            }
-        } else {
-        constexpr int CH = E < 4 ? E : 4;
-        int row0 = t;
-#pragma unroll 1
-        for (int ch = 0; ch < E / CH; ++ch) {
-            float2 self[CH];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) self[j] = valid ? __ldcg(sp + j * rowStride) : make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const int row = row0 + T * j;
+            for (unsigned q = 0; q < R; ++q) {
+                const int row = (int)(f0 + (L / R) * q);
                 const float qr = wavenumber(row, sRow, stepRow);
                 const float qr2 = CUPSS_FMUL(qr, qr);
-                const float q2 = CUPSS_FADD(CUPSS_FADD(qx2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
-                float2 val = kstage_point_scalar_q2(ks.sq2, ks.dt, q2, v[j], self[j]);
-                if (fixSelf && ((row == 0) || (2 * row == sRow))) val.y = 0.0f;
-                if (valid) dp[j * rowStride] = val;
+                const float q2a = CUPSS_FADD(CUPSS_FADD(qxa2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
+                const float q2b = CUPSS_FADD(CUPSS_FADD(qxb2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
+                float2 va, vb;
+                if constexpr (SIG >= 0) {
+                    va = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
+                    vb = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2b, x1[q], make_float2(self[q].z, self[q].w));
+                } else {
+                    va = kstage_point_scalar_q2(ks.sq2, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
+                    vb = kstage_point_scalar_q2(ks.sq2, dt, q2b, x1[q], make_float2(self[q].z, self[q].w));
+                }
+                const bool rowSelf = (row == 0) || (2 * row == sRow);
+                if (fixSelfA && rowSelf) va.y = 0.0f;
+                if (fixSelfB && rowSelf) vb.y = 0.0f;
+                if (!valid1) vb = make_float2(0.0f, 0.0f);   // padding column of the pitch
+                if (valid) st4(dp + q * rowStride, make_float4(va.x, va.y, vb.x, vb.y));
                 const int nr = row > sRow / 2 ? sRow - row : row;
-                v[j] = (keepFix && nr <= cutRow) ? val : make_float2(0.0f, 0.0f);
+                const bool keepR = nr <= cutRow;
+                x0[q] = (keepA && keepR) ? va : make_float2(0.0f, 0.0f);
+                x1[q] = (keepB && keepR) ? vb : make_float2(0.0f, 0.0f);
             }
-            if (E > CH) {   // rotate: v[i] <- v[i + CH]
-                float2 tmp[CH];
+        } else {
+#pragma unroll 1
+            for (unsigned q = 0; q < R; ++q) {
+                const int row = (int)(f0 + (L / R) * q);
+                const int iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0);
+                const int iz = a.axis == 2 ? row : 0;
+                const long long off = (long long)(kbase + (unsigned)row * krs);
+                const float2 ra = valid ? kstage_point(ks, make_kpoint(ks, (int)col, iy, iz), x0[0], off, step) : make_float2(0.0f, 0.0f);
+                const float2 rb = valid1 ? kstage_point(ks, make_kpoint(ks, (int)col + 1, iy, iz), x1[0], off + 1, step) : make_float2(0.0f, 0.0f);
+                // rotate so that the loop body only ever touches register 0 and R-1 (rolled loop, static indices)
 #pragma unroll
-                for (int j = 0; j < CH; ++j) tmp[j] = v[j];
-#pragma unroll
-                for (int i2 = 0; i2 < E - CH; ++i2) v[i2] = v[i2 + CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) v[E - CH + j] = tmp[j];
+                for (unsigned i = 0; i + 1 < R; ++i) { x0[i] = x0[i + 1]; x1[i] = x1[i + 1]; }
+                x0[R - 1] = ra; x1[R - 1] = rb;
             }
-            row0 += T * CH;
-            sp += CH * rowStride;
-            dp += CH * rowStride;
         }
-        }
-    } else {
-        const unsigned int step = ks.stepCounter ? *ks.stepCounter : 0u;
+
+        if (doInv) {
+            level_butterfly2<L, LAST, +1, false>(x0, x1, 0, twS);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int row = t + T * e;
-            const int iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0);
-            const int iz = a.axis == 2 ? row : 0;
-            if (valid) {
-                const KPoint k = make_kpoint(ks, col, iy, iz);
-                // k-space arrays share the natural addressing of the pass output
-                v[e] = kstage_point(ks, k, v[e], axis_off(a.aout, b, row, col), step);
-            } else {
-                v[e] = make_float2(0.0f, 0.0f);
+            for (unsigned q = 0; q < R; ++q) {
+                const float4 t = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
+                if constexpr (n > 1) tile[(v * R + q) * CP + cp] = t;
+                else if (valid) st4(axis_dst(a, lbase, pbase, v * R + q), t);
             }
         }
     }
 
-    if (ks.hasInv) {
-        if (a.pruneOn) {   // CTA-uniform: every mode of this tile is masked out -> nothing to transform or store
-            const int nyT = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
-            if (ct * C > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
-        }
-        if (ks.hasFwd && P::R1 > 1) __syncthreads();   // exchange buffer still being read by the forward transform
-        fft_line<L, +1>(v, t, a.tw, ex);
-        if (valid) {
-            if (a.pushOn) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) *axis_dst(a, b, t + T * e, col) = v[e];
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) a.out[axis_off(a.aout, b, t + T * e, col)] = v[e];
-            }
+    // ---- inverse levels n-2 .. 0
+    if constexpr (n > 1) {
+        if (doInv) {
+            auto gst = [&](unsigned pos, unsigned, float4 v) {
+                if (valid) st4(axis_dst(a, lbase, pbase, pos), v);
+            };
+            __syncthreads();
+            if constexpr (n >= 4) { tile_level<L, 2, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 3) { tile_level<L, 1, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            tile_level<L, 0, +1, TV>(tv, twS, sld, gst);
         }
     }
 }
@@ -263,21 +343,33 @@ __global__ void xgpu_barrier_kernel(const XBarrier b) {
 }
 
 // ---------------------------------------------------------------- dispatch
+template <class K>
+static cudaError_t set_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaSuccess;
+}
+
 template <int L>
 static cudaError_t launch_plain_L(int dir, const AxisArgs& a, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        if (AxisCfg<L>::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(axis_plain_kernel<L, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(axis_plain_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = set_smem(axis_plain_kernel<L, -1, false>, AxisCfg<L>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = set_smem(axis_plain_kernel<L, 1, false>, AxisCfg<L>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = set_smem(axis_plain_kernel<L, 1, true>, AxisCfg<L>::SMEM);
+        if (e != cudaSuccess) return e;
         attr = true;
     }
     const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
-    if (dir < 0) axis_plain_kernel<L, -1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
-    else axis_plain_kernel<L, 1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+    if (dir < 0) {
+        if (a.maskOn) return cudaErrorInvalidValue;   // the mask only exists on inverse transforms
+        axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+    } else if (a.maskOn) {
+        axis_plain_kernel<L, 1, true><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+    } else {
+        axis_plain_kernel<L, 1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -285,17 +377,15 @@ template <int L>
 static cudaError_t launch_kstage_L(const AxisArgs& a, const KStageD& ks, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        if (AxisCfg<L>::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_GENERIC, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+        cudaError_t e = set_smem(axis_kstage_kernel<L, KS_GENERIC, -1>, AxisCfg<L>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = set_smem(axis_kstage_kernel<L, KS_SCALAR_Q2, -1>, AxisCfg<L>::SMEM);
+        if (e != cudaSuccess) return e;
+        if constexpr (L >= 64) {
+            e = set_smem(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD>, AxisCfg<L>::SMEM);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
+            e = set_smem(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION>, AxisCfg<L>::SMEM);
             if (e != cudaSuccess) return e;
-            if constexpr (L >= 64) {
-                e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
-                if (e != cudaSuccess) return e;
-                e = cudaFuncSetAttribute(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AxisCfg<L>::SMEM);
-                if (e != cudaSuccess) return e;
-            }
         }
         attr = true;
     }
@@ -345,6 +435,15 @@ int axis_tile_cols(int L) {
 }
 
 bool fft_size_supported(int n) { return axis_tile_cols(n) != 0; }
+
+int host_level_twiddles(int L, float2* out) {
+    switch (L) {
+#define X(N) case N: fill_level_twiddles<N, 0>(out); return TwTable<N>::LEN;
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return 0;
+}
 
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st) {
     xgpu_barrier_kernel<<<1, 32, 0, st>>>(b);

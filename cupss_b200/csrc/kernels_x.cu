@@ -8,186 +8,350 @@
 // transformed as ONE complex line c = a + i b of sx points (no half-length untangling twiddles):
 //   inverse: C[k] = A[k] + i B[k] (k <= sx/2),  C[sx-k] = conj(A[k]) + i conj(B[k])
 //   forward: A[k] = (C[k] + conj C[sx-k]) / 2,   B[k] = (C[k] - conj C[sx-k]) / (2i)
-// T = sx/E threads per job, several jobs per CTA; consecutive lanes own consecutive points so every
-// global access is a contiguous run of T float2.
+// A "slot" is two jobs whose complex lines are interleaved element-wise in shared memory (float4 = the same
+// point of both jobs): every shared access is 128 bits wide and every twiddle is loaded once for two lines.
+// The transform runs in place on the slot's line, level by level (fft_core.cuh):
+//   inverse as decimation in frequency (natural order in, digit-reversed out), the pointwise real-space stage
+//   on the digit-reversed order (it does not care), forward as decimation in time (digit-reversed in, natural
+//   out); the innermost level of both and the products are fused on registers.
 #include "kernels.h"
 
 namespace cupss {
 
-template <int SX>
-struct LineEx {
-    float2* buf;
-    __device__ __forceinline__ static int p(int idx) {
-        constexpr int R0 = FftPlan<SX>::R0;
-        return idx + idx / R0;   // stride R0+1 float2 between butterflies of the first pass: conflict-free
-    }
-    __device__ __forceinline__ void st(int idx, float2 v) { buf[p(idx)] = v; }
-    __device__ __forceinline__ float2 ld(int idx) const { return buf[p(idx)]; }
-    __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-
 template <int SX> struct XCfg {
-    static constexpr int XB = SX + SX / FftPlan<SX>::R0 + 1;   // padded exchange line (float2)
+    static constexpr int XB = SX + SX / 8 + 1;                      // padded line (float4 elements)
+    static constexpr int NVMAX = SX / FftLevels<SX>::min_rad();     // most virtual threads per line any level has
+    static constexpr int TWF4 = (TwTable<SX>::LEN + 1) / 2;         // level twiddle table, in float4 units
 };
+// one pad element per 8: the innermost level (stride 8 elements between lanes) and the outer levels are conflict-free
+__device__ __forceinline__ unsigned xpad(unsigned idx) { return idx + (idx >> 3); }
 
-template <int SX, int MODE, bool FAST>
-__global__ void __launch_bounds__(256) xpass_kernel(const __grid_constant__ XArgs a) {
-    using P = FftPlan<SX>;
-    constexpr int E = P::E, T = P::T, XB = XCfg<SX>::XB;
-    extern __shared__ float2 smem[];
-    const int jl = threadIdx.x / T, t = threadIdx.x % T;
-    const long long job = (long long)blockIdx.x * a.jobsPerCta + jl;
-    const long long lineA = 2 * job, lineB = 2 * job + 1;
-    const bool hasA = lineA < a.nlines, hasB = lineB < a.nlines;
-    float2* xb = smem + (size_t)jl * a.perJobFloat2;
-    float2* stash = xb + XB;
-    LineEx<SX> ex{xb};
+constexpr int X_THREADS = 256;
 
-    float2 v[E];
+// SLOTS > 0: slots per CTA known at compile time (no stash: the line buffer is the whole slot); 0: run-time (XArgs).
+template <int SX, int MODE, bool FAST, int SLOTS>
+__global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __grid_constant__ XArgs a) {
+    using F = FftLevels<SX>;
+    constexpr int n = F::n, LAST = n - 1, XB = XCfg<SX>::XB;
+    using GL = LevelGeom<SX, LAST>;
+    constexpr unsigned RL = GL::R;
+    extern __shared__ float4 smem4[];
+    float2* twS = reinterpret_cast<float2*>(smem4);
+    float4* bufs = smem4 + XCfg<SX>::TWF4;
+    const unsigned S = SLOTS > 0 ? (unsigned)SLOTS : (unsigned)a.jobsPerCta;            // slots per CTA
+    const unsigned per = SLOTS > 0 ? (unsigned)XB : (unsigned)a.perJobFloat2;           // float4 elements per slot (line + stash)
+    const unsigned tid = threadIdx.x;
 
-    // ------------------------------------------------ inverse part (C2R of every input)
-    if (MODE != X_R2C_ONLY) {
-        for (int g = 0; g < a.nIn; ++g) {
-            const float2* pa = a.in[g] + lineA * a.pitch;
-            const float2* pb = a.in[g] + lineB * a.pitch;
+    for (unsigned i = tid; i < (unsigned)TwTable<SX>::LEN; i += X_THREADS) twS[i] = __ldg(a.tw + i);
+    __syncthreads();
+
+    using std::integral_constant;
+    using Plus = integral_constant<int, 1>;
+    using Minus = integral_constant<int, -1>;
+    using Dif = integral_constant<bool, true>;
+    using Dit = integral_constant<bool, false>;
+
+    // lines of slot s: job0 = (A0, B0), job1 = (A1, B1)
+    auto line0 = [&](unsigned s) -> long long { return 4ll * ((long long)blockIdx.x * S + s); };
+
+    // Source lines of slot s for input g: pointers to the four half-spectrum lines (A0, B0, A1, B1) and which of them exist.
+    struct SlotSrc { const float2* p[4]; bool v[4]; int kmax; };
+    auto slot_src = [&](int g, unsigned s) -> SlotSrc {
+        SlotSrc r;
+        const long long l0 = line0(s);
+        const float2* base = a.in[g] + l0 * a.pitch;
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int idx = t + T * e;
-                const int k = idx <= SX / 2 ? idx : SX - idx;
-                const bool live = k <= a.kmax[g];
-                float2 A = (hasA && live) ? __ldg(pa + k) : make_float2(0.0f, 0.0f);
-                float2 B = (hasB && live) ? __ldg(pb + k) : make_float2(0.0f, 0.0f);
-                if (k == 0 || 2 * k == SX) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of self-conjugate bins
-                if (idx > SX / 2) { A.y = -A.y; B.y = -B.y; }
-                v[e] = make_float2(A.x - B.y, A.y + B.x);
+        for (int i = 0; i < 4; ++i) { r.v[i] = l0 + i < a.nlines; r.p[i] = base + (unsigned)(i * a.pitch); }
+        r.kmax = a.kmax[g];
+        return r;
+    };
+    // C[idx] of both jobs (float4: job0 in xy, job1 in zw).
+    //   HALF = 0: idx <= sx/2 known (k = idx, no conjugation); 1: idx > sx/2 known (k = sx - idx, conjugated); 2: decide at run time.
+    auto formC = [&](auto halfTag, const SlotSrc& src, unsigned idx) -> float4 {
+        constexpr int HALF = decltype(halfTag)::value;
+        const bool upper = HALF == 1 || (HALF == 2 && idx > SX / 2);
+        const unsigned k = upper ? SX - idx : idx;
+        const bool live = (int)k <= src.kmax;
+        const float2 z = make_float2(0.0f, 0.0f);
+        float2 A0 = (live && src.v[0]) ? __ldg(src.p[0] + k) : z;
+        float2 B0 = (live && src.v[1]) ? __ldg(src.p[1] + k) : z;
+        float2 A1 = (live && src.v[2]) ? __ldg(src.p[2] + k) : z;
+        float2 B1 = (live && src.v[3]) ? __ldg(src.p[3] + k) : z;
+        if (k == 0 || 2 * k == SX) { A0.y = 0.0f; B0.y = 0.0f; A1.y = 0.0f; B1.y = 0.0f; }   // real-part projection of self-conjugate bins
+        if (upper) return make_float4(A0.x + B0.y, B0.x - A0.y, A1.x + B1.y, B1.x - A1.y);   // conj(A) + i conj(B)
+        return make_float4(A0.x - B0.y, A0.y + B0.x, A1.x - B1.y, A1.y + B1.x);                // A + i B
+    };
+
+    // one in-place level over every slot of the CTA, shared -> shared
+    auto level_ss = [&](auto lvTag, auto signTag, auto difTag) {
+        constexpr int LV = decltype(lvTag)::value;
+        constexpr int SIGN = decltype(signTag)::value;
+        constexpr bool DIF = decltype(difTag)::value;
+        using G = LevelGeom<SX, LV>;
+        constexpr unsigned R = G::R, M = G::M, N = G::N, NV = G::NV;
+#pragma unroll 1
+        for (unsigned w = tid; w < S * NV; w += X_THREADS) {
+            const unsigned s = w / NV, v = w % NV;
+            const unsigned blk = v / M, j = v % M, row0 = blk * N + j;
+            float4* xb = bufs + s * per;
+            float2 x0[R], x1[R];
+#pragma unroll
+            for (unsigned q = 0; q < R; ++q) {
+                const float4 t = xb[xpad(row0 + M * q)];
+                x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
             }
-            if (g > 0 && P::R1 > 1) __syncthreads();
-            fft_line<SX, +1>(v, t, a.tw, ex);
+            level_butterfly2<SX, LV, SIGN, DIF>(x0, x1, j, twS);
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = cscale(v[e], a.norm);
-            if (MODE == X_C2R_ONLY) {
+            for (unsigned q = 0; q < R; ++q) xb[xpad(row0 + M * q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
+        }
+    };
+
+    // ------------------------------------------------ R2C only (upload): real lines in, forward DIF, untangle from the digit-reversed order
+    if constexpr (MODE == X_R2C_ONLY) {
+        {
+            using G = LevelGeom<SX, 0>;
+            constexpr unsigned R = G::R, M = G::M, NV = G::NV;
+#pragma unroll 1
+            for (unsigned w = tid; w < S * NV; w += X_THREADS) {
+                const unsigned s = w / NV, v = w % NV;
+                const long long l0 = line0(s);
+                float4* xb = bufs + s * per;
+                float2 x0[R], x1[R];
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int x = t + T * e;
-                    if (hasA) a.realOut[lineA * SX + x] = v[e].x;
-                    if (hasB) a.realOut[lineB * SX + x] = v[e].y;
+                for (unsigned q = 0; q < R; ++q) {
+                    const unsigned x = v + M * q;
+                    x0[q].x = l0 < a.nlines ? __ldg(a.realIn + l0 * SX + x) : 0.0f;
+                    x0[q].y = l0 + 1 < a.nlines ? __ldg(a.realIn + (l0 + 1) * SX + x) : 0.0f;
+                    x1[q].x = l0 + 2 < a.nlines ? __ldg(a.realIn + (l0 + 2) * SX + x) : 0.0f;
+                    x1[q].y = l0 + 3 < a.nlines ? __ldg(a.realIn + (l0 + 3) * SX + x) : 0.0f;
                 }
-            } else if (!FAST) {
+                level_butterfly2<SX, 0, -1, true>(x0, x1, v, twS);
 #pragma unroll
-                for (int e = 0; e < E; ++e) stash[(size_t)g * SX + t + T * e] = v[e];
+                for (unsigned q = 0; q < R; ++q) xb[xpad(v + M * q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
             }
         }
-        if (MODE == X_C2R_ONLY) return;
+        __syncthreads();
+        if constexpr (n >= 2) { level_ss(integral_constant<int, 1>{}, Minus{}, Dif{}); __syncthreads(); }
+        if constexpr (n >= 3) { level_ss(integral_constant<int, 2>{}, Minus{}, Dif{}); __syncthreads(); }
+        if constexpr (n >= 4) { level_ss(integral_constant<int, 3>{}, Minus{}, Dif{}); __syncthreads(); }
     }
 
-    // ------------------------------------------------ products + forward part (R2C of every output)
-    const int nOut = MODE == X_R2C_ONLY ? 1 : a.nOut;
-    for (int o = 0; o < nOut; ++o) {
-        if (MODE == X_R2C_ONLY) {
+    // ------------------------------------------------ inverse part (C2R of every input), decimation in frequency
+    if constexpr (MODE != X_R2C_ONLY) {
+        for (int g = 0; g < a.nIn; ++g) {
+            if (g > 0) __syncthreads();   // line buffers are re-used per input
+            if constexpr (n > 1) {
+                using G = LevelGeom<SX, 0>;
+                constexpr unsigned R = G::R, M = G::M, NV = G::NV;
+#pragma unroll 1
+                for (unsigned w = tid; w < S * NV; w += X_THREADS) {
+                    const unsigned s = w / NV, v = w % NV;
+                    float4* xb = bufs + s * per;
+                    const SlotSrc src = slot_src(g, s);
+                    float2 x0[R], x1[R];
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int x = t + T * e;
-                v[e].x = hasA ? __ldg(a.realIn + lineA * SX + x) : 0.0f;
-                v[e].y = hasB ? __ldg(a.realIn + lineB * SX + x) : 0.0f;
-            }
-        } else if (FAST) {
-            // one input, one output, at most two monomials c*r^p with p <= 4: branch-free, straight from registers.
-            // r^p is the left-to-right product ((r*r)*r)*r of computeProduct (src/term.cpp:85-92).
-            const float c0 = a.mono[0].coef, c1 = a.nMono > 1 ? a.mono[1].coef : 0.0f;
-            const int p0 = a.mono[0].nfac, p1 = a.nMono > 1 ? a.mono[1].nfac : 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const float2 r = v[e];
-                const float2 r2 = make_float2(r.x * r.x, r.y * r.y);
-                const float2 r3 = make_float2(r2.x * r.x, r2.y * r.y);
-                const float2 r4 = make_float2(r3.x * r.x, r3.y * r.y);
-#define CUPSS_RP(p, c) ((p) == 0 ? 1.0f : ((p) == 1 ? r.c : ((p) == 2 ? r2.c : ((p) == 3 ? r3.c : r4.c))))
-                float2 acc = make_float2(c0 * CUPSS_RP(p0, x), c0 * CUPSS_RP(p0, y));
-                if (a.nMono > 1) { acc.x += c1 * CUPSS_RP(p1, x); acc.y += c1 * CUPSS_RP(p1, y); }
-#undef CUPSS_RP
-                v[e] = acc;
-            }
-        } else {
-            // real fields of every input are in the stash, point-aligned with this thread's registers
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int x = t + T * e;
-                float2 acc = make_float2(0.0f, 0.0f);
-                for (int m = 0; m < a.nMono; ++m) {
-                    if (a.mono[m].out != o) continue;
-                    float px = a.mono[m].coef, py = px;
-                    for (int f = 0; f < a.mono[m].nfac; ++f) {
-                        const float2 r = stash[(size_t)a.mono[m].fac[f] * SX + x];
-                        px *= r.x; py *= r.y;
+                    for (unsigned q = 0; q < R; ++q) {
+                        // v < M here, so which half of the spectrum the point lies in is known per q except on the q*M == sx/2 row
+                        float4 t;
+                        if (M * q < SX / 2u) t = formC(integral_constant<int, 0>{}, src, v + M * q);
+                        else if (M * q > SX / 2u) t = formC(integral_constant<int, 1>{}, src, v + M * q);
+                        else t = formC(integral_constant<int, 2>{}, src, v + M * q);
+                        x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
                     }
-                    acc.x += px; acc.y += py;
+                    level_butterfly2<SX, 0, +1, true>(x0, x1, v, twS);
+#pragma unroll
+                    for (unsigned q = 0; q < R; ++q) xb[xpad(v + M * q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
                 }
-                v[e] = acc;
+                __syncthreads();
+                if constexpr (n >= 3) { level_ss(integral_constant<int, 1>{}, Plus{}, Dif{}); __syncthreads(); }
+                if constexpr (n >= 4) { level_ss(integral_constant<int, 2>{}, Plus{}, Dif{}); __syncthreads(); }
+            }
+            // innermost level: real values appear on registers (position p <-> real index freq_of_pos(p))
+#pragma unroll 1
+            for (unsigned w = tid; w < S * GL::NV; w += X_THREADS) {
+                const unsigned s = w / GL::NV, v = w % GL::NV;
+                float4* xb = bufs + s * per;
+                SlotSrc src;
+                if constexpr (n == 1) src = slot_src(g, s);
+                float2 x0[RL], x1[RL];
+#pragma unroll
+                for (unsigned q = 0; q < RL; ++q) {
+                    float4 t;
+                    if constexpr (n > 1) t = xb[xpad(v * RL + q)];
+                    else t = formC(integral_constant<int, 2>{}, src, q);
+                    x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
+                }
+                level_butterfly2<SX, LAST, +1, true>(x0, x1, 0, twS);
+#pragma unroll
+                for (unsigned q = 0; q < RL; ++q) { x0[q] = cscale(x0[q], a.norm); x1[q] = cscale(x1[q], a.norm); }
+                if constexpr (MODE == X_C2R_ONLY) {
+                    // park the real values in place; written out in natural order below
+#pragma unroll
+                    for (unsigned q = 0; q < RL; ++q) xb[xpad(v * RL + q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
+                } else if constexpr (FAST) {
+                    // one input, one output, at most two monomials c*r^p with p <= 4: branch-free, straight from registers.
+                    // r^p is the left-to-right product ((r*r)*r)*r of computeProduct (src/term.cpp:85-92).
+                    const float c0 = a.mono[0].coef, c1 = a.nMono > 1 ? a.mono[1].coef : 0.0f;
+                    const int p0 = a.mono[0].nfac, p1 = a.nMono > 1 ? a.mono[1].nfac : 0;
+                    auto powr = [](float r, int p) -> float {
+                        const float r2 = r * r, r3 = r2 * r, r4 = r3 * r;
+                        return p == 0 ? 1.0f : (p == 1 ? r : (p == 2 ? r2 : (p == 3 ? r3 : r4)));
+                    };
+                    auto apply = [&](auto f) {
+#pragma unroll
+                        for (unsigned q = 0; q < RL; ++q) {
+                            x0[q] = make_float2(f(x0[q].x), f(x0[q].y));
+                            x1[q] = make_float2(f(x1[q].x), f(x1[q].y));
+                        }
+                    };
+                    // warp-uniform dispatch on the monomial pattern: the common single-monomial powers are straight-line code
+                    if (a.nMono == 1 && p0 == 3) apply([&](float r) { return c0 * ((r * r) * r); });
+                    else if (a.nMono == 1 && p0 == 2) apply([&](float r) { return c0 * (r * r); });
+                    else if (a.nMono == 1) apply([&](float r) { return c0 * powr(r, p0); });
+                    else apply([&](float r) { return c0 * powr(r, p0) + c1 * powr(r, p1); });
+                    level_butterfly2<SX, LAST, -1, false>(x0, x1, 0, twS);
+#pragma unroll
+                    for (unsigned q = 0; q < RL; ++q) xb[xpad(v * RL + q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
+                } else {
+                    float4* stash = xb + XB + (unsigned)g * XB;
+#pragma unroll
+                    for (unsigned q = 0; q < RL; ++q) stash[xpad(v * RL + q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
+                }
             }
         }
-        if (P::R1 > 1) __syncthreads();   // exchange buffer free (previous transform / previous untangle reads)
-        fft_line<SX, -1>(v, t, a.tw, ex);
-        // untangle the two real lines: needs C[sx-k], owned by another thread
+    }
+
+    if constexpr (MODE == X_C2R_ONLY) {
         __syncthreads();
+        const unsigned tps = X_THREADS / S;   // threads per slot (S divides X_THREADS)
+        const unsigned s = tid / tps;
+        const long long l0 = line0(s);
+        const float4* xb = bufs + s * per;
+        for (unsigned x = tid % tps; x < (unsigned)SX; x += tps) {
+            const float4 t = xb[xpad(pos_of_freq<SX>(x))];
+            if (l0 < a.nlines) a.realOut[l0 * SX + x] = t.x;
+            if (l0 + 1 < a.nlines) a.realOut[(l0 + 1) * SX + x] = t.y;
+            if (l0 + 2 < a.nlines) a.realOut[(l0 + 2) * SX + x] = t.z;
+            if (l0 + 3 < a.nlines) a.realOut[(l0 + 3) * SX + x] = t.w;
+        }
+        return;
+    }
+
+    // ------------------------------------------------ products + forward part (R2C of every output), decimation in time
+    const int nOut = (MODE == X_R2C_ONLY || FAST) ? 1 : a.nOut;
+    for (int o = 0; o < nOut; ++o) {
+        if constexpr (MODE == X_HOT && !FAST) {
+            // real fields of every input are in the stash, position-aligned with this thread's registers
+            __syncthreads();   // stash complete / previous output's untangle reads done
+#pragma unroll 1
+            for (unsigned w = tid; w < S * GL::NV; w += X_THREADS) {
+                const unsigned s = w / GL::NV, v = w % GL::NV;
+                float4* xb = bufs + s * per;
+                const float4* stash = xb + XB;
+                float2 x0[RL], x1[RL];
 #pragma unroll
-        for (int e = 0; e < E; ++e) ex.st(t + T * e, v[e]);
-        __syncthreads();
-        float2* qa = a.out[o] + lineA * a.pitch;
-        float2* qb = a.out[o] + lineB * a.pitch;
+                for (unsigned q = 0; q < RL; ++q) {
+                    const unsigned p = xpad(v * RL + q);
+                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int m = 0; m < a.nMono; ++m) {
+                        if (a.mono[m].out != o) continue;
+                        float4 pr = make_float4(a.mono[m].coef, a.mono[m].coef, a.mono[m].coef, a.mono[m].coef);
+                        for (int f = 0; f < a.mono[m].nfac; ++f) {
+                            const float4 r = stash[(unsigned)a.mono[m].fac[f] * XB + p];
+                            pr.x *= r.x; pr.y *= r.y; pr.z *= r.z; pr.w *= r.w;
+                        }
+                        acc.x += pr.x; acc.y += pr.y; acc.z += pr.z; acc.w += pr.w;
+                    }
+                    x0[q] = make_float2(acc.x, acc.y); x1[q] = make_float2(acc.z, acc.w);
+                }
+                level_butterfly2<SX, LAST, -1, false>(x0, x1, 0, twS);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int idx = t + T * e;
-            if (idx <= SX / 2) {
-                const float2 Cm = ex.ld((SX - idx) % SX);
-                const float2 Ck = v[e];
-                const float2 S = make_float2(Ck.x + Cm.x, Ck.y - Cm.y);   // C + conj(Cm)
-                const float2 D = make_float2(Ck.x - Cm.x, Ck.y + Cm.y);   // C - conj(Cm)
-                if (hasA) qa[idx] = make_float2(0.5f * S.x, 0.5f * S.y);
-                if (hasB) qb[idx] = make_float2(0.5f * D.y, -0.5f * D.x);
+                for (unsigned q = 0; q < RL; ++q) xb[xpad(v * RL + q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
+            }
+        }
+        if constexpr (MODE == X_HOT) {
+            __syncthreads();
+            if constexpr (n >= 4) { level_ss(integral_constant<int, 2>{}, Minus{}, Dit{}); __syncthreads(); }
+            if constexpr (n >= 3) { level_ss(integral_constant<int, 1>{}, Minus{}, Dit{}); __syncthreads(); }
+            if constexpr (n >= 2) { level_ss(integral_constant<int, 0>{}, Minus{}, Dit{}); __syncthreads(); }
+        }
+        // untangle the two real lines of each job: needs C[k] and C[sx-k]; two neighbouring k per thread (128-bit stores)
+        {
+            const unsigned tps = X_THREADS / S;
+            const unsigned s = tid / tps;
+            const long long l0 = line0(s);
+            const float4* xb = bufs + s * per;
+            float2* q0 = a.out[o] + l0 * a.pitch;
+            auto at = [&](unsigned k) -> float4 {   // C[k mod SX] of both jobs
+                const unsigned kk = k & (SX - 1);
+                return xb[xpad(MODE == X_R2C_ONLY ? pos_of_freq<SX>(kk) : kk)];
+            };
+            auto split = [&](float4 Ck, float4 Cm, float2& A0, float2& B0, float2& A1, float2& B1) {
+                A0 = make_float2(0.5f * (Ck.x + Cm.x), 0.5f * (Ck.y - Cm.y));     // (C + conj Cm) / 2
+                B0 = make_float2(0.5f * (Ck.y + Cm.y), -0.5f * (Ck.x - Cm.x));    // (C - conj Cm) / (2i)
+                A1 = make_float2(0.5f * (Ck.z + Cm.z), 0.5f * (Ck.w - Cm.w));
+                B1 = make_float2(0.5f * (Ck.w + Cm.w), -0.5f * (Ck.z - Cm.z));
+            };
+            for (unsigned k = 2 * (tid % tps); k <= SX / 2; k += 2 * tps) {
+                float2 A0, B0, A1, B1, A0n, B0n, A1n, B1n;
+                split(at(k), at(SX - k), A0, B0, A1, B1);
+                if (k + 1 <= SX / 2) {
+                    split(at(k + 1), at(SX - k - 1), A0n, B0n, A1n, B1n);
+                    if (l0 < a.nlines) *reinterpret_cast<float4*>(q0 + k) = make_float4(A0.x, A0.y, A0n.x, A0n.y);
+                    if (l0 + 1 < a.nlines) *reinterpret_cast<float4*>(q0 + a.pitch + k) = make_float4(B0.x, B0.y, B0n.x, B0n.y);
+                    if (l0 + 2 < a.nlines) *reinterpret_cast<float4*>(q0 + 2 * a.pitch + k) = make_float4(A1.x, A1.y, A1n.x, A1n.y);
+                    if (l0 + 3 < a.nlines) *reinterpret_cast<float4*>(q0 + 3 * a.pitch + k) = make_float4(B1.x, B1.y, B1n.x, B1n.y);
+                } else {
+                    if (l0 < a.nlines) q0[k] = A0;
+                    if (l0 + 1 < a.nlines) q0[a.pitch + k] = B0;
+                    if (l0 + 2 < a.nlines) q0[2 * a.pitch + k] = A1;
+                    if (l0 + 3 < a.nlines) q0[3 * a.pitch + k] = B1;
+                }
             }
         }
     }
 }
 
 // ---------------------------------------------------------------- dispatch
+template <int SX> struct XSlots {   // one virtual thread per real thread on the widest level
+    static constexpr int RAW = X_THREADS / XCfg<SX>::NVMAX;
+    static constexpr int V = RAW < 1 ? 1 : (RAW > 64 ? 64 : RAW);
+};
+
 template <int SX, int MODE, bool FAST>
 static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
-    using P = FftPlan<SX>;
-    constexpr int T = P::T, XB = XCfg<SX>::XB;
-    const int stashLines = (MODE == X_HOT && !FAST) ? a.nIn : 0;
-    const int perJob = XB + stashLines * SX;
-    const size_t budget = 96 * 1024;
-    int jobs = 256 / T;
-    if (jobs < 1) jobs = 1;
-    while (jobs > 1 && (size_t)jobs * perJob * sizeof(float2) > budget) jobs >>= 1;
-    const size_t smem = (size_t)jobs * perJob * sizeof(float2);
-    if (smem > 200 * 1024 || jobs * T > 256) return cudaErrorInvalidValue;
+    constexpr int XB = XCfg<SX>::XB;
+    constexpr bool STASH = (MODE == X_HOT && !FAST);
+    constexpr int CT = STASH ? 0 : XSlots<SX>::V;
+    const int stashLines = STASH ? a.nIn : 0;
+    const int perSlot = XB * (1 + stashLines);                      // float4 elements
+    const size_t budget = 72 * 1024;
+    int slots = XSlots<SX>::V;
+    while (slots > 1 && (size_t)slots * perSlot * sizeof(float4) > budget) slots >>= 1;
+    const size_t smem = ((size_t)XCfg<SX>::TWF4 + (size_t)slots * perSlot) * sizeof(float4);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(xpass_kernel<SX, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(xpass_kernel<SX, MODE, FAST, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    a.jobsPerCta = jobs;
-    a.perJobFloat2 = perJob;
-    const long long njobs = (a.nlines + 1) / 2;
-    const unsigned grid = (unsigned)((njobs + jobs - 1) / jobs);
-    xpass_kernel<SX, MODE, FAST><<<grid, jobs * T, smem, st>>>(a);
+    a.jobsPerCta = slots;
+    a.perJobFloat2 = perSlot;
+    const long long nslots = (a.nlines + 3) / 4;
+    const unsigned grid = (unsigned)((nslots + slots - 1) / slots);
+    xpass_kernel<SX, MODE, FAST, CT><<<grid, X_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int SX>
 static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
-    if constexpr (FftPlan<SX>::T > 256) {
-        return cudaErrorInvalidValue;
-    } else {
-        if (mode == X_C2R_ONLY) return launch_x<SX, X_C2R_ONLY, true>(a, st);
-        if (mode == X_R2C_ONLY) return launch_x<SX, X_R2C_ONLY, true>(a, st);
-        bool fast = a.nIn == 1 && a.nOut == 1 && a.nMono >= 1 && a.nMono <= 2;
-        for (int m = 0; m < a.nMono && fast; ++m) fast = a.mono[m].nfac <= 4;
-        if (fast) return launch_x<SX, X_HOT, true>(a, st);
-        return launch_x<SX, X_HOT, false>(a, st);
-    }
+    if (mode == X_C2R_ONLY) return launch_x<SX, X_C2R_ONLY, true>(a, st);
+    if (mode == X_R2C_ONLY) return launch_x<SX, X_R2C_ONLY, true>(a, st);
+    bool fast = a.nIn == 1 && a.nOut == 1 && a.nMono >= 1 && a.nMono <= 2;
+    for (int m = 0; m < a.nMono && fast; ++m) fast = a.mono[m].nfac <= 4;
+    if (fast) return launch_x<SX, X_HOT, true>(a, st);
+    return launch_x<SX, X_HOT, false>(a, st);
 }
 
 cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st) {

@@ -1,5 +1,8 @@
-// Host-side check of cupss_b200/csrc/fft_core.cuh: runs the SAME butterflies and Stockham index
-// arithmetic the kernels use, thread by thread on the CPU, against a double-precision naive DFT.
+// Host-side check of cupss_b200/csrc/fft_core.cuh: runs the SAME level butterflies, twiddles and index
+// arithmetic the kernels use, virtual thread by virtual thread on the CPU, against a double-precision naive DFT.
+//   forward: natural order in -> position p holds frequency freq_of_pos(p)
+//   inverse: that order in    -> natural order out (unnormalised)
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -7,45 +10,79 @@
 #include "../../cupss_b200/csrc/fft_core.cuh"
 using namespace cupss;
 
-template <int L, int DIR>
-double check() {
-    using P = FftPlan<L>;
-    constexpr int E = P::E, T = P::T, R0 = P::R0, R1 = P::R1, R2 = P::R2;
-    std::vector<float2> tw(L), x(L), buf(L), y(L);
-    for (int k = 0; k < L; ++k) tw[k] = make_float2((float)std::cos(-2.0 * kPi * k / L), (float)std::sin(-2.0 * kPi * k / L));
-    for (int i = 0; i < L; ++i) x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
-    std::vector<std::vector<float2>> regs(T, std::vector<float2>(E));
-    auto asarr = [&](int t) -> float2(&)[E] { return *reinterpret_cast<float2(*)[E]>(regs[t].data()); };
-    for (int t = 0; t < T; ++t) for (int e = 0; e < E; ++e) regs[t][e] = x[t + T * e];
-    for (int t = 0; t < T; ++t) stockham_pass<L, E, R0, 1, DIR>(asarr(t), t, tw.data());
-    if (R1 > 1) {
-        for (int t = 0; t < T; ++t) for (int e = 0; e < E; ++e) buf[stockham_out_index<L, E, R0, 1>(t, e)] = regs[t][e];
-        for (int t = 0; t < T; ++t) for (int e = 0; e < E; ++e) regs[t][e] = buf[t + T * e];
-        for (int t = 0; t < T; ++t) stockham_pass<L, E, R1, R0, DIR>(asarr(t), t, tw.data());
-        if (R2 > 1) {
-            for (int t = 0; t < T; ++t) for (int e = 0; e < E; ++e) buf[stockham_out_index<L, E, R1, R0>(t, e)] = regs[t][e];
-            for (int t = 0; t < T; ++t) for (int e = 0; e < E; ++e) regs[t][e] = buf[t + T * e];
-            for (int t = 0; t < T; ++t) stockham_pass<L, E, R2, R0 * R1, DIR>(asarr(t), t, tw.data());
-        }
+template <int L, int LV, int SIGN, bool DIF>
+void run_level(std::vector<float2>& buf, const float2* tw) {
+    using G = LevelGeom<L, LV>;
+    for (int v = 0; v < G::NV; ++v) {
+        const int blk = v / G::M, j = v % G::M, row0 = blk * G::N + j;
+        float2 x[G::R];
+        for (int q = 0; q < G::R; ++q) x[q] = buf[row0 + G::M * q];
+        level_butterfly<L, LV, SIGN, DIF>(x, j, tw);
+        for (int q = 0; q < G::R; ++q) buf[row0 + G::M * q] = x[q];
     }
-    for (int t = 0; t < T; ++t) for (int e = 0; e < E; ++e) y[t + T * e] = regs[t][e];
-    double err = 0, nrm = 0;
-    for (int k = 0; k < L; ++k) {
-        double re = 0, im = 0;
+}
+template <int L, int LV, int SIGN>
+void dif_from(std::vector<float2>& buf, const float2* tw) {   // natural in -> digit-reversed out
+    if constexpr (LV < FftLevels<L>::n) { run_level<L, LV, SIGN, true>(buf, tw); dif_from<L, LV + 1, SIGN>(buf, tw); }
+}
+template <int L, int LV, int SIGN>
+void dit_from(std::vector<float2>& buf, const float2* tw) {   // digit-reversed in -> natural out
+    if constexpr (LV >= 0) { run_level<L, LV, SIGN, false>(buf, tw); dit_from<L, LV - 1, SIGN>(buf, tw); }
+}
+
+template <int L>
+void naive(const std::vector<float2>& x, int dir, std::vector<double>& re, std::vector<double>& im) {
+    re.assign(L, 0); im.assign(L, 0);
+    for (int k = 0; k < L; ++k)
         for (int n = 0; n < L; ++n) {
-            double a = DIR * 2.0 * kPi * (double)((long)k * n % L) / L;
-            re += x[n].x * std::cos(a) - x[n].y * std::sin(a);
-            im += x[n].x * std::sin(a) + x[n].y * std::cos(a);
+            const double a = dir * 2.0 * kPi * (double)((long)k * n % L) / L;
+            re[k] += x[n].x * std::cos(a) - x[n].y * std::sin(a);
+            im[k] += x[n].x * std::sin(a) + x[n].y * std::cos(a);
         }
-        err += (re - y[k].x) * (re - y[k].x) + (im - y[k].y) * (im - y[k].y);
-        nrm += re * re + im * im;
+}
+
+template <int L>
+bool check() {
+    std::vector<float2> tw(TwTable<L>::LEN), x(L);
+    fill_level_twiddles<L, 0>(tw.data());
+    for (int i = 0; i < L; ++i) x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<double> re, im;
+    // permutation is a bijection
+    std::vector<int> seen(L, 0);
+    for (int p = 0; p < L; ++p) seen[freq_of_pos<L>(p)]++;
+    for (int k = 0; k < L; ++k) if (seen[k] != 1) { printf("L=%d: freq_of_pos is not a permutation\n", L); return false; }
+    double worst = 0;
+    for (int sign = -1; sign <= 1; sign += 2) {
+        naive<L>(x, sign, re, im);
+        // DIF: natural in, position p holds frequency freq_of_pos(p)
+        std::vector<float2> buf = x;
+        if (sign < 0) dif_from<L, 0, -1>(buf, tw.data()); else dif_from<L, 0, +1>(buf, tw.data());
+        double err = 0, nrm = 0;
+        for (int p = 0; p < L; ++p) {
+            const int k = freq_of_pos<L>(p);
+            if ((int)pos_of_freq<L>(k) != p) { printf("L=%d: pos_of_freq is not the inverse of freq_of_pos\n", L); return false; }
+            err += (re[k] - buf[p].x) * (re[k] - buf[p].x) + (im[k] - buf[p].y) * (im[k] - buf[p].y);
+            nrm += re[k] * re[k] + im[k] * im[k];
+        }
+        const double e1 = std::sqrt(err / nrm);
+        // DIT: input index n at position pos_of_freq(n), natural order out
+        for (int nn = 0; nn < L; ++nn) buf[pos_of_freq<L>(nn)] = x[nn];
+        if (sign < 0) dit_from<L, FftLevels<L>::n - 1, -1>(buf, tw.data()); else dit_from<L, FftLevels<L>::n - 1, +1>(buf, tw.data());
+        err = 0; nrm = 0;
+        for (int k = 0; k < L; ++k) {
+            err += (re[k] - buf[k].x) * (re[k] - buf[k].x) + (im[k] - buf[k].y) * (im[k] - buf[k].y);
+            nrm += re[k] * re[k] + im[k] * im[k];
+        }
+        const double e2 = std::sqrt(err / nrm);
+        printf("L=%5d  sign %+d  DIF %.3e  DIT %.3e\n", L, sign, e1, e2);
+        worst = std::max(worst, std::max(e1, e2));
     }
-    return std::sqrt(err / nrm);
+    return worst < 5e-7;
 }
 
 int main() {
     int bad = 0;
-#define CHK(L) { double a = check<L, -1>(), b = check<L, 1>(); printf("L=%5d  fwd %.3e  inv %.3e\n", L, a, b); if (!(a < 5e-7 && b < 5e-7)) bad++; }
+#define CHK(L) if (!check<L>()) bad++;
     CHK(1) CHK(2) CHK(4) CHK(8) CHK(16) CHK(32) CHK(64) CHK(128) CHK(256) CHK(512) CHK(1024) CHK(2048) CHK(4096) CHK(8192)
     printf(bad ? "FAIL\n" : "OK\n");
     return bad;
