@@ -50,6 +50,32 @@ __device__ __forceinline__ float2* axis_dst(const AxisArgs& a, float2* lbase, un
 __device__ __forceinline__ float4 ld4(const float2* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed): the whole input tile of a CTA is put in flight by
+// its first few instructions, with no register staging, so the HBM latency is paid once per tile and overlaps the
+// arithmetic of the other CTAs resident on the SM.
+__device__ __forceinline__ void cp_async16(float4* smemDst, const float2* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Tile prologue: position p of the tile <- row rowOf(p) of the input (natural order for a forward transform, frequency
+// order for an inverse one).  Rows that are known zeros (keep(row) false) and invalid column pairs are zero-filled.
+template <int L, int CP, int TV, class RowOf, class Keep>
+__device__ __forceinline__ void tile_fetch(float4* tile, unsigned tv, unsigned cp, bool valid, const float2* ibase, const AxisAddr& ain,
+                                           RowOf rowOf, Keep keep) {
+#pragma unroll 4
+    for (unsigned p = tv; p < (unsigned)L; p += TV) {
+        const unsigned row = rowOf(p);
+        float4* dst = tile + p * CP + cp;
+        if (valid && keep(row)) cp_async16(dst, ibase + row_off(ain, row));
+        else *dst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
 // One level over the tile: every real thread walks its virtual threads (v = tv, tv + TV, ...).
 //   ld(pos, frow) -> float4, st(pos, frow, value);  pos = position inside the tile, frow = frequency row that
 //   position holds in the digit-reversed order (only meaningful on the innermost level, M == 1).
@@ -92,8 +118,9 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
         const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
         if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
     }
-    for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
-    __syncthreads();
+    auto load_twiddles = [&]() {
+        for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
+    };
 
     const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
     float2* lbase = a.out + (b * (unsigned)a.aout.bs + col);
@@ -101,9 +128,12 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     // rows beyond rowCut (|n| > rowCut) are known zeros: not loaded.  rowCut < 0: off.
     const unsigned keepLo = a.rowCut >= 0 ? (unsigned)a.rowCut : (unsigned)L, keepHi = a.rowCut >= 0 ? (unsigned)(L - a.rowCut) : 0u;
 
-    auto gload = [&](unsigned row) -> float4 {
-        if (!(valid && (row <= keepLo || row >= keepHi))) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        float4 t = ld4(ibase + row_off(a.ain, row));
+    auto keepRow = [&](unsigned row) -> bool { return row <= keepLo || row >= keepHi; };
+    auto gload = [&](unsigned row) -> float4 {   // direct path (single-level transforms, no tile)
+        if (!(valid && keepRow(row))) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return ld4(ibase + row_off(a.ain, row));
+    };
+    auto masked = [&](float4 t, unsigned row) -> float4 {
         if constexpr (MASK) {
             const int iy = a.axis == 2 ? a.kyBase + (int)b : (a.axis == 1 ? (int)row : 0);
             const int iz = a.axis == 2 ? (int)row : 0;
@@ -119,24 +149,33 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
 
     if constexpr (DIR < 0) {   // forward: natural rows in, frequency rows out
-        auto gld = [&](unsigned pos, unsigned) -> float4 { return gload(pos); };
         auto gst = [&](unsigned, unsigned frow, float4 v) { gstore(frow, v); };
         if constexpr (n == 1) {
+            auto gld = [&](unsigned pos, unsigned) -> float4 { return gload(pos); };
             tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
         } else {
-            tile_level<L, 0, DIR, TV>(tv, twS, gld, sst);
+            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, keepRow);
+            load_twiddles();
+            cp_async_wait_all();
+            __syncthreads();
+            tile_level<L, 0, DIR, TV>(tv, twS, sld, sst);
             __syncthreads();
             if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
             if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
             tile_level<L, n - 1, DIR, TV>(tv, twS, sld, gst);
         }
     } else {                   // inverse: frequency rows in, natural rows out
-        auto gld = [&](unsigned, unsigned frow) -> float4 { return gload(frow); };
         auto gst = [&](unsigned pos, unsigned, float4 v) { gstore(pos, v); };
         if constexpr (n == 1) {
+            auto gld = [&](unsigned, unsigned frow) -> float4 { return masked(gload(frow), frow); };
             tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
         } else {
-            tile_level<L, n - 1, DIR, TV>(tv, twS, gld, sst);
+            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return freq_of_pos<L>(p); }, keepRow);
+            load_twiddles();
+            cp_async_wait_all();
+            __syncthreads();
+            auto mld = [&](unsigned pos, unsigned frow) -> float4 { return masked(tile[pos * CP + cp], frow); };
+            tile_level<L, n - 1, DIR, TV>(tv, twS, mld, sst);
             __syncthreads();
             if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
             if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
@@ -176,6 +215,9 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
     float2* lbase = a.out + kbase;
     const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
 
+    if constexpr (n > 1) {
+        if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
+    }
     for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
     if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
         // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
@@ -183,6 +225,7 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
         for (unsigned r = threadIdx.x; r < (unsigned)L; r += Cfg::THREADS)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + r * krs));
     }
+    cp_async_wait_all();
     __syncthreads();
 
     auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
@@ -191,10 +234,7 @@ axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ K
     // ---- forward levels 0 .. n-2 (the last level is fused with the k stage below)
     if (ks.hasFwd) {
         if constexpr (n > 1) {
-            auto gld = [&](unsigned pos, unsigned) -> float4 {
-                return valid ? ld4(ibase + row_off(a.ain, pos)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            };
-            tile_level<L, 0, -1, TV>(tv, twS, gld, sst);
+            tile_level<L, 0, -1, TV>(tv, twS, sld, sst);
             __syncthreads();
             if constexpr (n >= 3) { tile_level<L, 1, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
             if constexpr (n >= 4) { tile_level<L, 2, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
