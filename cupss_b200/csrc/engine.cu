@@ -194,6 +194,23 @@ struct cupss_b200_plan {
         *out = d;
         return CUPSS_B200_OK;
     }
+    // twiddles of the two-level x kernel (key -sx in the same cache); *out = nullptr when that kernel does not cover sx
+    int get_twiddle_x3(const float2** out) {
+        *out = nullptr;
+        const char* no = getenv("CUPSS_B200_NO_X3");
+        if ((no && no[0] == '1') || !xpass3_supported(sx)) return CUPSS_B200_OK;
+        auto it = twiddles.find(-sx);
+        if (it != twiddles.end()) { *out = it->second; return CUPSS_B200_OK; }
+        std::vector<float2> h(sx, make_float2(1.0f, 0.0f));
+        if (host_x3_twiddles(sx, h.data()) <= 0) return CUPSS_B200_OK;
+        float2* d = nullptr;
+        CK(cudaMalloc(&d, sizeof(float2) * sx));
+        CK(cudaMemcpyAsync(d, h.data(), sizeof(float2) * sx, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        twiddles[-sx] = d;
+        *out = d;
+        return CUPSS_B200_OK;
+    }
     int get_scratch(size_t idx, float2** out) {
         while (scratch.size() <= idx) scratch.push_back(nullptr);
         if (!scratch[idx]) {
@@ -570,6 +587,7 @@ struct cupss_b200_plan {
             x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
             x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
             CKR(get_twiddle(sx, &x.xa.tw));
+            CKR(get_twiddle_x3(&x.xa.tw3));
             x.bytes = (inFrac + x.xa.nOut) * spec_bytes();
             xl.push_back(x);
             g0 = g1;

@@ -80,6 +80,7 @@ struct XArgs {
     long long nlines;
     float norm;      // 1 / (sx*sy*sz)
     const float2* tw;
+    const float2* tw3;     // strided-level twiddles of the two-level kernel (kernels_x3.cu); null: not available
     float* realOut;        // mode C2R_ONLY: [nlines][sx]
     const float* realIn;   // mode R2C_ONLY
     int jobsPerCta;
@@ -98,6 +99,10 @@ cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
 // Level twiddle table of an L-point transform (fft_core.cuh); returns the number of entries written (<= L), 0 if unsupported.
 int host_level_twiddles(int L, float2* out);
+// Two-level x pass (kernels_x3.cu): sizes it covers, its twiddle table (<= sx entries) and its launcher.
+bool xpass3_supported(int sx);
+int host_x3_twiddles(int sx, float2* out);
+cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st);
 bool fft_size_supported(int n);
 
 }  // namespace cupss

@@ -327,7 +327,8 @@ static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
     const int perSlot = XB * (1 + stashLines);                      // float4 elements
     const size_t budget = 72 * 1024;
     int slots = XSlots<SX>::V;
-    while (slots > 1 && (size_t)slots * perSlot * sizeof(float4) > budget) slots >>= 1;
+    if (CT == 0)   // run-time slot count (stash path): shrink to the shared-memory budget; CT > 0 is baked into the kernel
+        while (slots > 1 && (size_t)slots * perSlot * sizeof(float4) > budget) slots >>= 1;
     const size_t smem = ((size_t)XCfg<SX>::TWF4 + (size_t)slots * perSlot) * sizeof(float4);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static size_t attr = 0;
@@ -350,6 +351,7 @@ static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
     if (mode == X_R2C_ONLY) return launch_x<SX, X_R2C_ONLY, true>(a, st);
     bool fast = a.nIn == 1 && a.nOut == 1 && a.nMono >= 1 && a.nMono <= 2;
     for (int m = 0; m < a.nMono && fast; ++m) fast = a.mono[m].nfac <= 4;
+    if (fast && a.tw3 && xpass3_supported(SX) && a.nMono == 1 && (a.mono[0].nfac == 2 || a.mono[0].nfac == 3)) return launch_xpass3(SX, a, st);
     if (fast) return launch_x<SX, X_HOT, true>(a, st);
     return launch_x<SX, X_HOT, false>(a, st);
 }

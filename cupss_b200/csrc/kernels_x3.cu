@@ -1,0 +1,195 @@
+// kernels_x3.cu -- two-level variant of the contiguous-axis pass for sx = R0 * 2R0 (512 = 16*32, 128 = 8*16), used when
+// the real-space stage is one output of one input (the Cahn-Hilliard / Allen-Cahn / Swift-Hohenberg class).
+//
+// Same algorithm as kernels_x.cu (two real lines as one complex line, inverse as decimation in frequency, pointwise
+// real-space stage, forward as decimation in time), restructured around the resource that bounds that kernel --
+// shared-memory bandwidth (profiles/r01d: l1tex 78 %, 5 shared-memory round trips per point):
+//   * two levels instead of three: radix R0 on the strided level, radix R1 = 2*R0 on the innermost (contiguous) level,
+//     whose inverse butterfly, normalisation, product and forward butterfly are fused on registers;
+//   * a thread owns BOTH members j and M-j of every mirror pair of the strided level, so C[k] and C[sx-k] are formed
+//     from one load of A[k], B[k] on the way in and untangled on registers on the way out: no exchange for the untangle
+//     and half the global load instructions;
+//   => 2 shared-memory round trips per point.
+// Replaces the same reference code as kernels_x.cu (/root/reference/src/field.cpp:247-298, src/term.cpp:48-102).
+#include "kernels.h"
+
+namespace cupss {
+
+template <int SX> struct X3Cfg {
+    static constexpr int R0 = SX == 512 ? 16 : (SX == 128 ? 8 : 0);
+    static constexpr int R1 = 2 * R0;             // innermost radix = stride M of the strided level
+    static constexpr int M = R1;
+    static constexpr int TL = R0;                 // threads per job (complex line): M/2 mirror pairs == R0 innermost blocks
+    static constexpr int THREADS = 256;
+    static constexpr int JOBS = THREADS / TL;
+    static constexpr int LB = SX + 2 * R0;        // padded line, float2 elements: two pad elements after every R1
+    static constexpr int TWLEN = (R0 - 1) * M;    // strided-level twiddles: entry (q-1)*M + j = exp(-2*pi*i*j*q/SX)
+    static constexpr size_t SMEM = ((size_t)TWLEN + (size_t)JOBS * LB) * sizeof(float2);
+};
+
+template <int SX>
+__device__ __forceinline__ unsigned x3pad(unsigned idx) { return idx + 2u * (idx / (unsigned)X3Cfg<SX>::R1); }
+
+template <int SX>
+__global__ void __launch_bounds__(X3Cfg<SX>::THREADS, 2) xpass3_kernel(const __grid_constant__ XArgs a) {
+    using Cfg = X3Cfg<SX>;
+    constexpr int R0 = Cfg::R0, R1 = Cfg::R1, M = Cfg::M, TL = Cfg::TL, LB = Cfg::LB, H = R0 / 2;
+    extern __shared__ float2 smem2[];
+    float2* twS = smem2;
+    const unsigned tid = threadIdx.x, job = tid / TL, t = tid % TL;
+    float2* xb = smem2 + Cfg::TWLEN + job * LB;
+
+    for (unsigned i = tid; i < (unsigned)Cfg::TWLEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw3 + i);
+
+    const long long jg = (long long)blockIdx.x * Cfg::JOBS + job;
+    const long long lA = 2 * jg, lB = lA + 1;
+    const bool hasA = lA < a.nlines, hasB = lB < a.nlines;
+    const bool t0 = t == 0;
+    const unsigned jA = t0 ? 0u : t, jB = t0 ? (unsigned)(M / 2) : (unsigned)M - t;   // the thread's two rows of the strided level
+    const float2 z = make_float2(0.0f, 0.0f);
+
+    float2 xA[R0], xB[R0];
+
+    // ------------------------------------------------ inverse, strided level: form C from the half-spectrum lines
+    {
+        const float2* pa = a.in[0] + lA * a.pitch;
+        const float2* pb = a.in[0] + lB * a.pitch;
+        const int kmax = a.kmax[0];
+        float2 mA[H], mB[H];
+        auto form = [&](unsigned k, float2& c, float2& m) {   // c = A[k] + i B[k],  m = conj(A[k]) + i conj(B[k]) = C[sx - k]
+            const bool live = (int)k <= kmax;
+            float2 A = (live && hasA) ? __ldg(pa + k) : z;
+            float2 B = (live && hasB) ? __ldg(pb + k) : z;
+            if (k == 0 || 2 * k == SX) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of self-conjugate bins
+            c = make_float2(A.x - B.y, A.y + B.x);
+            m = make_float2(A.x + B.y, B.x - A.y);
+        };
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+            form(jA + M * q, xA[q], mA[q]);
+            form(jB + M * q, xB[q], mB[q]);
+        }
+        float2 cMid = z, mMid;
+        if (t0) form(SX / 2, cMid, mMid);   // k = sx/2 belongs to row 0 (register H of the thread that owns rows 0 and M/2)
+        // mirrors: rows (j, M - j) for t >= 1; row 0 mirrors onto itself and so does row M/2 for t == 0
+#pragma unroll
+        for (int i = 0; i < H; ++i) xB[H + i] = t0 ? mB[H - 1 - i] : mA[H - 1 - i];
+        xA[H] = t0 ? cMid : mB[H - 1];
+#pragma unroll
+        for (int i = 1; i < H; ++i) xA[H + i] = t0 ? mA[H - i] : mB[H - 1 - i];
+    }
+    Dft<R0, +1>::run(xA);
+    Dft<R0, +1>::run(xB);
+    __syncthreads();   // twiddle table complete
+#pragma unroll
+    for (int q = 1; q < R0; ++q) {
+        xA[q] = cmul_conj(xA[q], twS[(q - 1) * M + jA]);
+        xB[q] = cmul_conj(xB[q], twS[(q - 1) * M + jB]);
+    }
+#pragma unroll
+    for (int q = 0; q < R0; ++q) {
+        xb[x3pad<SX>(jA + M * q)] = xA[q];
+        xb[x3pad<SX>(jB + M * q)] = xB[q];
+    }
+    __syncthreads();
+
+    // ------------------------------------------------ innermost level: inverse butterfly, product, forward butterfly
+    {
+        float2 y[R1];
+        float4* blk = reinterpret_cast<float4*>(xb + t * (R1 + 2));   // block t: R1 contiguous points (16-byte aligned)
+#pragma unroll
+        for (int i = 0; i < R1 / 2; ++i) {
+            const float4 v = blk[i];
+            y[2 * i] = make_float2(v.x, v.y); y[2 * i + 1] = make_float2(v.z, v.w);
+        }
+        Dft<R1, +1>::run(y);
+        const float norm = a.norm;
+        const float c0 = a.mono[0].coef;
+        const bool cube = a.mono[0].nfac == 3;   // the launcher only sends single monomials c*r^2 / c*r^3 here (warp-uniform)
+        // r^3 is the left-to-right product (r*r)*r of computeProduct (src/term.cpp:85-92)
+        if (cube) {
+#pragma unroll
+            for (int i = 0; i < R1; ++i) {
+                const float rx = y[i].x * norm, ry = y[i].y * norm;
+                y[i] = make_float2(c0 * ((rx * rx) * rx), c0 * ((ry * ry) * ry));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R1; ++i) {
+                const float rx = y[i].x * norm, ry = y[i].y * norm;
+                y[i] = make_float2(c0 * (rx * rx), c0 * (ry * ry));
+            }
+        }
+        Dft<R1, -1>::run(y);
+#pragma unroll
+        for (int i = 0; i < R1 / 2; ++i) blk[i] = make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------ forward, strided level (twiddle, butterfly) + untangle on registers
+#pragma unroll
+    for (int q = 0; q < R0; ++q) {
+        xA[q] = xb[x3pad<SX>(jA + M * q)];
+        xB[q] = xb[x3pad<SX>(jB + M * q)];
+    }
+#pragma unroll
+    for (int q = 1; q < R0; ++q) {
+        xA[q] = cmul(xA[q], twS[(q - 1) * M + jA]);
+        xB[q] = cmul(xB[q], twS[(q - 1) * M + jB]);
+    }
+    Dft<R0, -1>::run(xA);
+    Dft<R0, -1>::run(xB);
+    // xA[r] = C[jA + M r], xB[r] = C[jB + M r];  A[k] = (C[k] + conj C[sx-k]) / 2,  B[k] = (C[k] - conj C[sx-k]) / (2i)
+    float2* qa = a.out[0] + lA * a.pitch;
+    float2* qb = a.out[0] + lB * a.pitch;
+    auto emit = [&](unsigned k, float2 Ck, float2 Cm) {
+        if (hasA) qa[k] = make_float2(0.5f * (Ck.x + Cm.x), 0.5f * (Ck.y - Cm.y));
+        if (hasB) qb[k] = make_float2(0.5f * (Ck.y + Cm.y), -0.5f * (Ck.x - Cm.x));
+    };
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+        const float2 CmA = t0 ? xA[(R0 - r) % R0] : xB[R0 - 1 - r];
+        const float2 CmB = t0 ? xB[R0 - 1 - r] : xA[R0 - 1 - r];
+        emit(jA + M * r, xA[r], CmA);
+        emit(jB + M * r, xB[r], CmB);
+    }
+    if (t0) emit(SX / 2, xA[H], xA[H]);
+}
+
+template <int SX>
+static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
+    using Cfg = X3Cfg<SX>;
+    static bool attr = false;
+    if (!attr) {
+        if (Cfg::SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        attr = true;
+    }
+    const long long njobs = (a.nlines + 1) / 2;
+    const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
+    xpass3_kernel<SX><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+bool xpass3_supported(int sx) { return sx == 512 || sx == 128; }
+
+cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st) {
+    if (sx == 512) return launch_x3_size<512>(a, st);
+    if (sx == 128) return launch_x3_size<128>(a, st);
+    return cudaErrorInvalidValue;
+}
+
+int host_x3_twiddles(int sx, float2* out) {
+    if (!xpass3_supported(sx)) return 0;
+    const int R0 = sx == 512 ? 16 : 8, M = 2 * R0;
+    for (int q = 1; q < R0; ++q)
+        for (int j = 0; j < M; ++j) {
+            const double ang = -2.0 * kPi * (double)((j * q) % sx) / (double)sx;
+            out[(q - 1) * M + j] = make_float2((float)__builtin_cos(ang), (float)__builtin_sin(ang));
+        }
+    return (R0 - 1) * M;
+}
+
+}  // namespace cupss

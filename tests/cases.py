@@ -54,6 +54,16 @@ CASES = {
                     ic=dict(phi=("smooth", (0.5, 0.05))), steps=100),
     "ch3d_64x32x16": dict(shape=(64, 32, 16), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
                           ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
+    # the two-level x kernel (kernels_x3.cu) covers sx = 128 and 512: same systems on grids with those x extents
+    "ch3d_128x16x16": dict(shape=(128, 16, 16), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                           ic=dict(phi=("smooth", (0.5, 0.05))), steps=100),
+    "ch2d_512x16": dict(shape=(512, 16, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                        ic=dict(phi=("smooth", (0.4, 0.04))), steps=100),
+    "ch3d_512x8x8": dict(shape=(512, 8, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                         ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
+    # quadratic nonlinearity through the same kernel (single monomial c*r^2)
+    "burgers_like_128": dict(shape=(128, 32, 1), dt=0.01, fields=[("u", 1)], params=dict(nu=0.5), eqs=["dt u + nu*q^2*u = -0.5*iqx*u^2"],
+                             ic=dict(u=("smooth", (0.5, 0.05))), steps=100),
     # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
     "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),
