@@ -533,6 +533,7 @@ struct cupss_b200_plan {
             std::vector<int> ins;
             size_t g1 = g0;
             int nMono = 0;
+            const size_t maxIn = (size_t)xpass_max_inputs(sx);
             while (g1 < groups.size()) {
                 std::vector<int> trial = ins;
                 int monos = nMono;
@@ -544,8 +545,8 @@ struct cupss_b200_plan {
                         if (!seen) trial.push_back(fid);
                     }
                 }
-                if (g1 > g0 && (trial.size() > (size_t)XP_MAX_IN || monos > XP_MAX_MONO || g1 - g0 >= (size_t)XP_MAX_OUT)) break;
-                if (trial.size() > (size_t)XP_MAX_IN || monos > XP_MAX_MONO) return fail(CUPSS_B200_ERR_ARG, "a single term group needs too many fields/monomials");
+                if (g1 > g0 && (trial.size() > maxIn || monos > XP_MAX_MONO || g1 - g0 >= (size_t)XP_MAX_OUT)) break;
+                if (trial.size() > maxIn || monos > XP_MAX_MONO) return fail(CUPSS_B200_ERR_ARG, "a single term group needs too many fields/monomials for sx = %d (at most %zu fields)", sx, maxIn);
                 ins = trial; nMono = monos; ++g1;
             }
             x.xa.nIn = (int)ins.size();
@@ -771,6 +772,9 @@ struct cupss_b200_plan {
             ks.nout++;
         }
         ks.hasInv = invField >= 0 ? 1 : 0;
+        ks.usesInvq = 0;
+        for (int i = 0; i < npres; ++i) if (ks.pres[i].invq) ks.usesInvq = 1;
+        for (int o = 0; o < ks.nout; ++o) if (ks.out[o].noisy && ks.out[o].noise.invq) ks.usesInvq = 1;
         // lean evaluator when the sweep is a single noise-free dynamic field whose prefactors depend on q^2 only
         ks.fastKind = KS_GENERIC;
         if (ks.nout == 1 && ks.out[0].dynamic && !ks.out[0].noisy && ks.nsrc == 1 && extraInv.empty() && nterm <= 1 &&

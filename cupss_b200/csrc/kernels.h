@@ -94,6 +94,7 @@ enum XMode { X_HOT = 0, X_C2R_ONLY = 1, X_R2C_ONLY = 2 };
 cudaError_t launch_axis_plain(int L, int dir, const AxisArgs& a, cudaStream_t st);
 cudaError_t launch_axis_kstage(int L, const AxisArgs& a, const KStageD& ks, cudaStream_t st);
 cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st);
+int xpass_max_inputs(int sx);   // inputs one launch can take (shared-memory stash)
 cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L

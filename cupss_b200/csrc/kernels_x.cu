@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
     const unsigned S = SLOTS > 0 ? (unsigned)SLOTS : (unsigned)a.jobsPerCta;            // slots per CTA
     const unsigned per = SLOTS > 0 ? (unsigned)XB : (unsigned)a.perJobFloat2;           // float4 elements per slot (line + stash)
     const unsigned tid = threadIdx.x;
+    const unsigned NT = SLOTS > 0 ? (unsigned)X_THREADS : blockDim.x;   // the stash path sizes its CTAs to the slots that fit
 
-    for (unsigned i = tid; i < (unsigned)TwTable<SX>::LEN; i += X_THREADS) twS[i] = __ldg(a.tw + i);
+    for (unsigned i = tid; i < (unsigned)TwTable<SX>::LEN; i += NT) twS[i] = __ldg(a.tw + i);
     __syncthreads();
 
     using std::integral_constant;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
         using G = LevelGeom<SX, LV>;
         constexpr unsigned R = G::R, M = G::M, N = G::N, NV = G::NV;
 #pragma unroll 1
-        for (unsigned w = tid; w < S * NV; w += X_THREADS) {
+        for (unsigned w = tid; w < S * NV; w += NT) {
             const unsigned s = w / NV, v = w % NV;
             const unsigned blk = v / M, j = v % M, row0 = blk * N + j;
             float4* xb = bufs + s * per;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
             using G = LevelGeom<SX, 0>;
             constexpr unsigned R = G::R, M = G::M, NV = G::NV;
 #pragma unroll 1
-            for (unsigned w = tid; w < S * NV; w += X_THREADS) {
+            for (unsigned w = tid; w < S * NV; w += NT) {
                 const unsigned s = w / NV, v = w % NV;
                 const long long l0 = line0(s);
                 float4* xb = bufs + s * per;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
                 using G = LevelGeom<SX, 0>;
                 constexpr unsigned R = G::R, M = G::M, NV = G::NV;
 #pragma unroll 1
-                for (unsigned w = tid; w < S * NV; w += X_THREADS) {
+                for (unsigned w = tid; w < S * NV; w += NT) {
                     const unsigned s = w / NV, v = w % NV;
                     float4* xb = bufs + s * per;
                     const SlotSrc src = slot_src(g, s);
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
             }
             // innermost level: real values appear on registers (position p <-> real index freq_of_pos(p))
 #pragma unroll 1
-            for (unsigned w = tid; w < S * GL::NV; w += X_THREADS) {
+            for (unsigned w = tid; w < S * GL::NV; w += NT) {
                 const unsigned s = w / GL::NV, v = w % GL::NV;
                 float4* xb = bufs + s * per;
                 SlotSrc src;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
 
     if constexpr (MODE == X_C2R_ONLY) {
         __syncthreads();
-        const unsigned tps = X_THREADS / S;   // threads per slot (S divides X_THREADS)
+        const unsigned tps = NT / S;   // threads per slot (S divides X_THREADS)
         const unsigned s = tid / tps;
         const long long l0 = line0(s);
         const float4* xb = bufs + s * per;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
             // real fields of every input are in the stash, position-aligned with this thread's registers
             __syncthreads();   // stash complete / previous output's untangle reads done
 #pragma unroll 1
-            for (unsigned w = tid; w < S * GL::NV; w += X_THREADS) {
+            for (unsigned w = tid; w < S * GL::NV; w += NT) {
                 const unsigned s = w / GL::NV, v = w % GL::NV;
                 float4* xb = bufs + s * per;
                 const float4* stash = xb + XB;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
         }
         // untangle the two real lines of each job: needs C[k] and C[sx-k]; two neighbouring k per thread (128-bit stores)
         {
-            const unsigned tps = X_THREADS / S;
+            const unsigned tps = NT / S;
             const unsigned s = tid / tps;
             const long long l0 = line0(s);
             const float4* xb = bufs + s * per;
@@ -325,10 +326,16 @@ static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
     constexpr int CT = STASH ? 0 : XSlots<SX>::V;
     const int stashLines = STASH ? a.nIn : 0;
     const int perSlot = XB * (1 + stashLines);                      // float4 elements
-    const size_t budget = 72 * 1024;
+    const size_t budget = 100 * 1024;   // two CTAs per SM
     int slots = XSlots<SX>::V;
-    if (CT == 0)   // run-time slot count (stash path): shrink to the shared-memory budget; CT > 0 is baked into the kernel
+    int threads = X_THREADS;
+    if (CT == 0) {   // run-time slot count (stash path): shrink to the shared-memory budget and size the CTA to it
         while (slots > 1 && (size_t)slots * perSlot * sizeof(float4) > budget) slots >>= 1;
+        threads = slots * XCfg<SX>::NVMAX;
+        if (threads > X_THREADS) threads = X_THREADS;
+        if (threads < 32) threads = 32;
+        while (threads % slots) ++threads;   // the untangle splits the CTA evenly over the slots
+    }
     const size_t smem = ((size_t)XCfg<SX>::TWF4 + (size_t)slots * perSlot) * sizeof(float4);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static size_t attr = 0;
@@ -341,7 +348,7 @@ static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
     a.perJobFloat2 = perSlot;
     const long long nslots = (a.nlines + 3) / 4;
     const unsigned grid = (unsigned)((nslots + slots - 1) / slots);
-    xpass_kernel<SX, MODE, FAST, CT><<<grid, X_THREADS, smem, st>>>(a);
+    xpass_kernel<SX, MODE, FAST, CT><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -354,6 +361,14 @@ static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
     if (fast && a.tw3 && xpass3_supported(SX) && a.nMono == 1 && (a.mono[0].nfac == 2 || a.mono[0].nfac == 3)) return launch_xpass3(SX, a, st);
     if (fast) return launch_x<SX, X_HOT, true>(a, st);
     return launch_x<SX, X_HOT, false>(a, st);
+}
+
+// Most inputs one x-pass launch can take for this line length: the real fields of all inputs of a slot are stashed in
+// shared memory next to the line buffer (one slot must fit in 200 KB).
+int xpass_max_inputs(int sx) {
+    const long long xb = (long long)sx + sx / 8 + 1;   // XCfg<SX>::XB
+    const long long fit = (200ll * 1024 - ((long long)sx * 8)) / (xb * (long long)sizeof(float4)) - 1;
+    return (int)(fit < 1 ? 1 : (fit > XP_MAX_IN ? XP_MAX_IN : fit));
 }
 
 cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st) {
