@@ -53,6 +53,7 @@ _SIGS = {
     "cupss_capi_initialize_half_system": (None, [C.c_void_p, C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_int]),
     "cupss_capi_initialize_from_file": (None, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char]),
     "cupss_capi_dump_plan": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "cupss_capi_set_mirror_callback": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
 }
 
 # entry points that only the product build of the facade exports (tools/cupss_capi.h, CUPSS_B200_PRODUCT)
@@ -82,6 +83,9 @@ _ENGINE_SIGS = {
     "cupss_b200_download_comp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cupss_b200_step": (C.c_int, [C.c_void_p, C.c_int]),
     "cupss_b200_sync": (C.c_int, [C.c_void_p]),
+    "cupss_b200_step_stage": (C.c_int, [C.c_void_p, C.c_int]),
+    "cupss_b200_real_view_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cupss_b200_real_view_commit": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "cupss_b200_field_alias": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cupss_b200_time_steps": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "cupss_b200_profile_step": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -299,6 +303,11 @@ class Evolver:
 
     def initializeFromFile(self, name, path, skiprows=1, delimiter=","):
         self._lib.cupss_capi_initialize_from_file(self._h, name.encode(), path.encode(), skiprows, delimiter.encode())
+
+    def setMirrorCallback(self, name: str, odd: bool = False):
+        """Install the facade's built-in host callback (mirror boundary condition) on a field of a RUN_CPU evolver."""
+        if self._lib.cupss_capi_set_mirror_callback(self._h, name.encode(), 1 if odd else 0) != 0:
+            raise KeyError(name)
 
     def dumpPlan(self) -> str:
         buf = C.create_string_buffer(1 << 16)

@@ -152,6 +152,8 @@ struct cupss_b200_plan {
     int dealiasRule = CUPSS_B200_DEALIAS_GPU_RULE;
     std::vector<Field> fields;
     std::vector<Launch> step;
+    size_t stageSplit = 0;     // step[0, stageSplit): constraint sweep; [stageSplit, end): dynamic sweep + counter bump
+    float2* viewBuf = nullptr; // float2[N] view of a real field handed to user callbacks
     std::vector<float2*> scratch;
     std::map<int, float2*> twiddles;
     float* realBuf = nullptr;
@@ -952,6 +954,7 @@ struct cupss_b200_plan {
         laneEv.clear();
         arenaNext = 0; nextPt = 0;
         CKR(build_stage(false, step));
+        stageSplit = step.size();
         CKR(build_stage(true, step));
         if (foldBarrier && nextPt == 1) return fail(CUPSS_B200_ERR_STATE, "internal: a single exchange point cannot order its own re-use");
         if (nextPt > XH_EPOCH / CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "too many exchange points (%d)", nextPt);
@@ -975,6 +978,60 @@ struct cupss_b200_plan {
         CK(e);
         CK(cudaGraphInstantiate(&graphExec, g, 0));
         CK(cudaGraphDestroy(g));
+        return CUPSS_B200_OK;
+    }
+
+    // One sweep class of one step, eagerly (user callbacks run between the sweeps; field::setRHS, src/field.cpp:68-86).
+    int do_stage(int which) {
+        if (!finalized) return fail(CUPSS_B200_ERR_STATE, "step before finalize");
+        const size_t b = which == 0 ? 0 : stageSplit, e = which == 0 ? stageSplit : step.size();
+        for (size_t i = b; i < e; ++i) CKR(run_launch(step[i]));
+        return CUPSS_B200_OK;
+    }
+    // Real view of a field for a callback: which = 0 the field itself, 1 its dealiased copy (what products read).
+    int view_begin(int f, int which, float2** dev) {
+        if (nranks != 1) return fail(CUPSS_B200_ERR_ARG, "user callbacks are single-GPU only");
+        Field& F = fields[f];
+        const size_t n = (size_t)sx * sy * zl;
+        if (!realBuf) CK(cudaMalloc(&realBuf, n * sizeof(float)));
+        if (!viewBuf) CK(cudaMalloc(&viewBuf, n * sizeof(float2)));
+        if (which == 0) {
+            if (!F.S) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
+            CKR(inverse_full(F.S));
+        } else {
+            if (!F.W2) return fail(CUPSS_B200_ERR_STATE, "field %s has no dealiased copy", F.name.c_str());
+            Launch x{};
+            x.kind = Launch::XPASS; x.mode = X_C2R_ONLY;
+            x.xa.nIn = 1; x.xa.in[0] = F.W2; x.xa.kmax[0] = ncol - 1;
+            x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
+            x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
+            x.xa.realOut = realBuf;
+            CKR(get_twiddle(sx, &x.xa.tw));
+            CKR(run_launch(x));
+        }
+        CK(launch_real_expand(realBuf, viewBuf, n, stream));
+        CK(cudaStreamSynchronize(stream));
+        *dev = viewBuf;
+        return CUPSS_B200_OK;
+    }
+    int view_commit(int f, int which) {
+        Field& F = fields[f];
+        const size_t n = (size_t)sx * sy * zl;
+        if (!viewBuf || !realBuf) return fail(CUPSS_B200_ERR_STATE, "view_commit without view_begin");
+        CK(cudaDeviceSynchronize());   // the callback's kernels run on the legacy default stream
+        CK(launch_real_compress(viewBuf, realBuf, n, stream));
+        if (which == 0) {
+            CKR(forward_full(F.S));
+        } else {
+            Launch x{};
+            x.kind = Launch::XPASS; x.mode = X_R2C_ONLY;
+            x.xa.nOut = 1; x.xa.out[0] = F.W2;
+            x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
+            x.xa.norm = (float)sy * (float)sz;   // real = W2-convention / (sx*sy*sz) and R2C(C2R(.)) = sx * (.)
+            x.xa.realIn = realBuf;
+            CKR(get_twiddle(sx, &x.xa.tw));
+            CKR(run_launch(x));
+        }
         return CUPSS_B200_OK;
     }
 
@@ -1038,6 +1095,7 @@ void cupss_b200_destroy(cupss_b200_plan* p) {
     for (float2* s : p->scratch) if (s) cudaFree(s);
     for (auto& kv : p->twiddles) cudaFree(kv.second);
     if (p->realBuf) cudaFree(p->realBuf);
+    if (p->viewBuf) cudaFree(p->viewBuf);
     if (p->stepCounter) cudaFree(p->stepCounter);
     for (int d = 0; d < p->nranks; ++d)
         if (d != p->rank && p->peerArena[d]) cudaIpcCloseMemHandle(p->peerArena[d]);
@@ -1206,6 +1264,22 @@ int cupss_b200_download_comp(cupss_b200_plan* p, int f, float* host) {
 int cupss_b200_step(cupss_b200_plan* p, int nsteps) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
     return p->do_steps(nsteps);
+}
+int cupss_b200_step_stage(cupss_b200_plan* p, int stage) {
+    if (!p || stage < 0 || stage > 1) return fail(CUPSS_B200_ERR_ARG, "bad stage");
+    return p->do_stage(stage);
+}
+int cupss_b200_real_view_begin(cupss_b200_plan* p, int f, int which, void** dev_float2) {
+    CKR(check_field(p, f));
+    if (!dev_float2 || which < 0 || which > 1) return fail(CUPSS_B200_ERR_ARG, "bad view request");
+    float2* d = nullptr;
+    CKR(p->view_begin(f, which, &d));
+    *dev_float2 = d;
+    return CUPSS_B200_OK;
+}
+int cupss_b200_real_view_commit(cupss_b200_plan* p, int f, int which) {
+    CKR(check_field(p, f));
+    return p->view_commit(f, which);
 }
 int cupss_b200_sync(cupss_b200_plan* p) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");

@@ -534,6 +534,21 @@ cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+__global__ void real_expand_kernel(const float* __restrict__ in, float2* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = make_float2(in[i], 0.0f);
+}
+__global__ void real_compress_kernel(const float2* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i].x;
+}
+cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStream_t st) {
+    real_expand_kernel<<<148 * 8, 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_real_compress(const float2* in, float* out, size_t n, cudaStream_t st) {
+    real_compress_kernel<<<148 * 8, 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st) {
     bump_counter_kernel<<<1, 1, 0, st>>>(counter);
     return cudaGetLastError();

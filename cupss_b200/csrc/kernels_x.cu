@@ -121,10 +121,12 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
 #pragma unroll
                 for (unsigned q = 0; q < R; ++q) {
                     const unsigned x = v + M * q;
-                    x0[q].x = l0 < a.nlines ? __ldg(a.realIn + l0 * SX + x) : 0.0f;
-                    x0[q].y = l0 + 1 < a.nlines ? __ldg(a.realIn + (l0 + 1) * SX + x) : 0.0f;
-                    x1[q].x = l0 + 2 < a.nlines ? __ldg(a.realIn + (l0 + 2) * SX + x) : 0.0f;
-                    x1[q].y = l0 + 3 < a.nlines ? __ldg(a.realIn + (l0 + 3) * SX + x) : 0.0f;
+                    // a.norm: 1 for a plain forward transform; the scale that turns real values back into the engine's
+                    // un-normalised W2 convention when a real view is committed (a power of two: exact)
+                    x0[q].x = l0 < a.nlines ? __ldg(a.realIn + l0 * SX + x) * a.norm : 0.0f;
+                    x0[q].y = l0 + 1 < a.nlines ? __ldg(a.realIn + (l0 + 1) * SX + x) * a.norm : 0.0f;
+                    x1[q].x = l0 + 2 < a.nlines ? __ldg(a.realIn + (l0 + 2) * SX + x) * a.norm : 0.0f;
+                    x1[q].y = l0 + 3 < a.nlines ? __ldg(a.realIn + (l0 + 3) * SX + x) * a.norm : 0.0f;
                 }
                 level_butterfly2<SX, 0, -1, true>(x0, x1, v, twS);
 #pragma unroll

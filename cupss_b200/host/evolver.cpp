@@ -8,6 +8,9 @@
 #include <ctime>
 #include <cstring>
 #include <iomanip>
+#include <vector>
+
+#include <cuda_runtime.h>
 
 #include "../../inc/cupss.h"
 #include "../../include/cupss_b200.h"
@@ -243,11 +246,41 @@ void evolver::prepareProblem() {
     if (verbose) std::cout << "Building the fused per-equation plan." << std::endl;
     sendSystemToEngine();
     for (field *f : fields) {
-        if (f->hasCB || f->hasCBFourier) {
-            std::cout << "ERROR: user callbacks (field " << f->name << ") are not supported by the B200 engine yet" << std::endl;
+        if (f->hasCBFourier) {
+            std::cout << "ERROR: Fourier-space callbacks (field " << f->name << ") are not supported by the B200 engine" << std::endl;
+            std::exit(1);
+        }
+        if (f->hasCB && partRanks > 1) {
+            std::cout << "ERROR: user callbacks (field " << f->name << ") need a single-GPU run" << std::endl;
             std::exit(1);
         }
         f->system_p = this;
+    }
+}
+
+// field::setRHS' callback hook (src/field.cpp:68-86): the user function sees the real field -- and, when products read the
+// field, its dealiased copy -- as float2[N] with the value in .x: a device pointer on the RUN_GPU path, the host array on
+// the RUN_CPU path.  Only flagged fields pay for the materialised view.
+void evolver::applyCallback(field *f) {
+    if (f->callback == NULL) {
+        std::cout << "Wants to apply callback function but pointer to function is NULL" << std::endl;
+        return;
+    }
+    const size_t n = (size_t)sx * sy * sz;
+    for (int which = 0; which < (f->needsaliasing ? 2 : 1); ++which) {
+        void *dev = nullptr;
+        engineCheck(cupss_b200_real_view_begin(plan, f->engine_id, which, &dev), "real_view_begin");
+        if (with_cuda) {
+            f->callback(this, static_cast<float2 *>(dev), sx, sy, sz);
+        } else {
+            std::vector<float2> tmp;
+            float2 *host = f->real_array;
+            if (which == 1) { tmp.resize(n); host = tmp.data(); }
+            if (cudaMemcpy(host, dev, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) engineCheck(2, "callback download");
+            f->callback(this, host, sx, sy, sz);
+            if (cudaMemcpy(dev, host, n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) engineCheck(2, "callback upload");
+        }
+        engineCheck(cupss_b200_real_view_commit(plan, f->engine_id, which), "real_view_commit");
     }
 }
 
@@ -258,7 +291,17 @@ int evolver::advanceTime() {
     }
     if (currentTimeStep % writeEveryNSteps == 0) writeOut();
     if (planDirty) sendSystemToEngine();
-    engineCheck(cupss_b200_step(plan, 1), "step");
+    bool anyCB = false;
+    for (field *f : fields) anyCB = anyCB || f->hasCB;
+    if (!anyCB) {
+        engineCheck(cupss_b200_step(plan, 1), "step");
+    } else {
+        // sweeps run eagerly with the callbacks in between, in the reference's order (constraint fields, then dynamic ones)
+        engineCheck(cupss_b200_step_stage(plan, 0), "step_stage");
+        for (field *f : fields) if (!f->dynamic && f->hasCB) applyCallback(f);
+        engineCheck(cupss_b200_step_stage(plan, 1), "step_stage");
+        for (field *f : fields) if (f->dynamic && f->hasCB) applyCallback(f);
+    }
     if (!with_cuda) {
         // reference-CPU semantics: host arrays are live after every step (examples/06_kpz reads them directly)
         for (field *f : fields) refreshHostMirror(f, true, true);

@@ -20,6 +20,8 @@
  *                                (= field::updateTerms/setRHS, term::update and the 12 extern "C" *_gpu
  *                                   launchers of inc/cupss/field_kernels.cuh:7-19, inc/cupss/term_kernels.cuh:7-15,
  *                                   plus every cufftExecC2C / curandGenerateNormal on that path)
+ *   cupss_b200_step_stage +      field::setRHS callback hook: callback(system, real_array_d, ...) and, for a field that
+ *   cupss_b200_real_view_*         products read, callback(system, real_dealiased_d, ...)             src/field.cpp:68-86
  *   cupss_b200_download_real     field::copyRealDeviceToHost (real_array)                    src/field.cpp:345-348
  *   cupss_b200_download_comp     field::copyDeviceToHost (comp_array)                        src/field.cpp:337-340
  *   cupss_b200_destroy           evolver/field/term dtors                                    src/evolver.cpp:40-45, src/field_init.cpp:156-189
@@ -78,6 +80,14 @@ int cupss_b200_download_real(cupss_b200_plan *p, int field, float *host_float2);
 int cupss_b200_download_comp(cupss_b200_plan *p, int field, float *host_float2);   /* full spectrum; nranks == 1 */
 
 int cupss_b200_step(cupss_b200_plan *p, int nsteps);   /* asynchronous on the plan's stream */
+
+/* User callbacks (boundary conditions).  A step is then driven as: step_stage(0) [constraint fields], callbacks of the
+ * constraint fields, step_stage(1) [dynamic fields + step counter], callbacks of the dynamic fields.  A callback sees
+ * float2[sz][sy][sx] on the device, value in .x (the reference's real_array_d): which = 0 the field, 1 its dealiased
+ * copy.  begin materialises the view and synchronises; commit waits for the device and transforms the view back. */
+int cupss_b200_step_stage(cupss_b200_plan *p, int stage);
+int cupss_b200_real_view_begin(cupss_b200_plan *p, int field, int which, void **dev_float2);
+int cupss_b200_real_view_commit(cupss_b200_plan *p, int field, int which);
 int cupss_b200_sync(cupss_b200_plan *p);
 
 /* Field flags computed by finalize (field::needsaliasing / aliasing_order, src/term_init.cpp:123-126). */

@@ -64,6 +64,15 @@ CASES = {
     # quadratic nonlinearity through the same kernel (single monomial c*r^2)
     "burgers_like_128": dict(shape=(128, 32, 1), dt=0.01, fields=[("u", 1)], params=dict(nu=0.5), eqs=["dt u + nu*q^2*u = -0.5*iqx*u^2"],
                              ic=dict(u=("smooth", (0.5, 0.05))), steps=100),
+    # user callbacks: mirror boundary conditions on a doubled domain, RUN_CPU flavour (host callbacks)
+    #   examples/07_inhomogeneous_diffusion: even BC on v and on the coefficient field x, products x*iqxv and x*v
+    "bc_even_inhomogeneous_64": dict(shape=(64, 64, 1), dt=0.002, fields=[("v", 1), ("iqxv", 0), ("x", 0)], params={},
+                                     eqs=["dt v +0.5*q^2*v = iqx*x*iqxv + x*iqy^2*v", "iqxv = iqx*v"],
+                                     ic=dict(v=("droplet", (1.0, 0.0, 8.0, 3.0, 16, 16, 0)), x=("smooth", (0.3, 0.0))), steps=30,
+                                     callbacks=[("v", False), ("x", False)], device=0, oracle="U"),
+    #   examples/08_neumann_dirichlet_bc: odd BC (Dirichlet) on a diffusing field
+    "bc_odd_diffusion_64": dict(shape=(64, 64, 1), dt=0.05, fields=[("phi", 1)], params={}, eqs=["dt phi + q^2*phi = 0"],
+                                ic=dict(phi=("droplet", (0.0, 1.0, 6.0, 2.0, 16, 16, 0))), steps=60, callbacks=[("phi", True)], device=0, oracle="U"),
     # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
     "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),
@@ -93,6 +102,8 @@ def build_system(case, lib=None, device=1):
         ev.addEquation(e)
     for f, a in case.get("noise", []):
         ev.addNoise(f, a)
+    for f, odd in case.get("callbacks", []):
+        ev.setMirrorCallback(f, odd)
     for name, (kind, args) in case["ic"].items():
         if kind == "smooth":
             ev.setReal(name, smooth_ic(sx, sy, sz, *args))

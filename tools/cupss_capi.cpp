@@ -115,6 +115,35 @@ static void put_pres(std::ostringstream &os, const pres &p)
     os << "{" << num << "," << p.q2n << "," << p.iqx << "," << p.iqy << "," << p.iqz << "," << p.invq << "}";
 }
 
+/* Built-in HOST callbacks for tests: mirror boundary conditions on a doubled 2-D domain (the construction of
+ * examples/07 and 08 of the reference, written from its description): the field on the quadrant i <= sx/2, j <= sy/2 is
+ * reflected into the other three with sign `parity` per reflection.  They are installed through the public members
+ * field::hasCB / field::callback exactly like a user's main() would (examples/08_neumann_dirichlet_bc). */
+static void mirror_apply(float2 *a, int sx, int sy, float parity)
+{
+    for (int j = 0; j < sy; ++j)
+        for (int i = 0; i < sx; ++i) {
+            const bool ri = i > sx / 2, rj = j > sy / 2;
+            if (!ri && !rj) continue;
+            const int si = ri ? sx - i : i, sj = rj ? sy - j : j;
+            float sign = 1.0f;
+            if (ri) sign *= parity;
+            if (rj) sign *= parity;
+            a[j * sx + i].x = sign * a[sj * sx + si].x;
+        }
+}
+static void mirror_even_cb(evolver *, float2 *a, int sx, int sy, int) { mirror_apply(a, sx, sy, 1.0f); }
+static void mirror_odd_cb(evolver *, float2 *a, int sx, int sy, int) { mirror_apply(a, sx, sy, -1.0f); }
+
+int cupss_capi_set_mirror_callback(void *ev, const char *name, int odd)
+{
+    if (EV(ev)->fieldsMap.find(name) == EV(ev)->fieldsMap.end()) return 1;
+    field *f = EV(ev)->fieldsMap[name];
+    f->hasCB = true;
+    f->callback = odd ? mirror_odd_cb : mirror_even_cb;
+    return 0;
+}
+
 int cupss_capi_dump_plan(void *ev, char *buf, int buflen)
 {
     evolver *e = EV(ev);

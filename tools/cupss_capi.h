@@ -43,6 +43,8 @@ void cupss_capi_initialize_droplet(void *ev, const char *name, float v_out, floa
 void cupss_capi_add_droplet(void *ev, const char *name, float value, float radius, float width, int cx, int cy, int cz);
 void cupss_capi_initialize_half_system(void *ev, const char *name, float v1, float v2, float width, int direction);
 void cupss_capi_initialize_from_file(void *ev, const char *name, const char *path, int skiprows, char delimiter);
+/* installs a built-in host callback (mirror boundary condition, even or odd) on a field: for RUN_CPU evolvers */
+int cupss_capi_set_mirror_callback(void *ev, const char *name, int odd);
 /* textual dump of the parsed system from public members (fields, implicit pres, terms, products, noise, aliasing) */
 int cupss_capi_dump_plan(void *ev, char *buf, int buflen);
 
