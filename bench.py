@@ -219,8 +219,12 @@ def main():
     per_launch_ms = kernels[top]["ms"] / kernels[top]["launches_per_step"]
     per_launch_bytes = kernels[top]["bytes"] / kernels[top]["launches_per_step"]
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from the committed ncu --set full capture
+    if world == 1 and os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(f"{n}", {}).get(top)
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": traffic, "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "per_kernel": {k: {"ms": round(v["ms"], 4), "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in kernels.items()},
                 "step_bytes": ev.bytesPerStep(), "step_GBps": ev.bytesPerStep() * value / 1e9,
                 "step_frac_of_peak": ev.bytesPerStep() * value / 1e9 / peak}

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_F = os.path.join(ROOT, "oracle", "_ref", "libcupss_ref_f.so")
 ORACLE_U = os.path.join(ROOT, "oracle", "_ref", "libcupss_ref_u.so")
 SHIM = os.path.join(ROOT, "oracle", "_ref", "libfftw_shim.so")
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "libcupss_ref_gpu.so")   # the reference's own cuFFT path (needs a GPU)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
