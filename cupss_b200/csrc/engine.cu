@@ -166,6 +166,7 @@ struct cupss_b200_plan {
     // available for experiments: CUPSS_B200_FOLD_BARRIER=1, CUPSS_B200_XCHUNKS=n.
     bool foldBarrier = false;
     int xchunks = 1;
+    int pushPadKB = 0;         // CUPSS_B200_PUSH_PAD_KB: extra shared memory per CTA of a chunked pushed y pass (occupancy cap)
     cudaGraphExec_t graphExec = nullptr;
     bool finalized = false;
     bool useGraph = true;
@@ -643,6 +644,7 @@ struct cupss_b200_plan {
                     y.bytes /= nchunk; y.commBytes /= nchunk;
                     if (nchunk > 1) {
                         y.lane = 1;
+                        y.ax.extraSmem = pushPadKB * 1024;
                         if (g == 0) y.waitEv = ev;
                         if (c + 1 == nchunk && g + 1 == yl.size()) { joinEv = new_event(); y.sigEv = joinEv; }
                     }
@@ -1133,6 +1135,8 @@ int cupss_b200_set_partition(cupss_b200_plan* p, int rank, int nranks, const voi
     p->foldBarrier = xk && xk[0] == '1';
     const char* xc = getenv("CUPSS_B200_XCHUNKS");
     if (xc && atoi(xc) >= 1) p->xchunks = atoi(xc);
+    const char* pp = getenv("CUPSS_B200_PUSH_PAD_KB");
+    if (pp && atoi(pp) >= 0) p->pushPadKB = atoi(pp);
     p->zl = p->sz / nranks; p->kyl = p->sy / nranks;
     p->specElems = (size_t)p->pitch * p->kyl * p->sz;   // == pitch * sy * zl
     return CUPSS_B200_OK;

@@ -46,6 +46,8 @@ struct AxisArgs {
     int sigOn, sigPt, rank, nranks;
     unsigned int sigTotal;
     int waitOn, waitPt;
+    int extraSmem;   // bytes of dynamic shared memory requested on top of the tile: caps the CTAs per SM of an NVLink-bound
+                     // pushed pass so that a pass on the other lane can share the SMs (0: off)
 };
 // Arena header layout (32-bit words from the arena base): flag table [pt][CUPSS_MAX_PEERS], epochs, error word, done counters.
 constexpr int XH_FLAGS = 0, XH_EPOCH = 1024, XH_ERROR = 2048, XH_DONE = 3072;
