@@ -1208,6 +1208,13 @@ static int ensure_real_buf(cupss_b200_plan* p) {
     return CUPSS_B200_OK;
 }
 
+static int ensure_view_buf(cupss_b200_plan* p) {
+    if (!p->viewBuf) CK(cudaMalloc(&p->viewBuf, (size_t)p->sx * p->sy * p->zl * sizeof(float2)));
+    return CUPSS_B200_OK;
+}
+
+// Host arrays keep the reference's float2 layout (value in .x); the float2 <-> float conversion and the reconstruction of
+// the full spectrum from the Hermitian half run on the device, so the host only sees two plain copies.
 int cupss_b200_upload_real(cupss_b200_plan* p, int f, const float* host) {
     CKR(check_field(p, f));
     if (!host) return fail(CUPSS_B200_ERR_ARG, "null host pointer");
@@ -1217,10 +1224,10 @@ int cupss_b200_upload_real(cupss_b200_plan* p, int f, const float* host) {
         CK(cudaMemsetAsync(F.S, 0, p->specElems * sizeof(float2), p->stream));
     }
     CKR(ensure_real_buf(p));
+    CKR(ensure_view_buf(p));
     const size_t n = (size_t)p->sx * p->sy * p->zl;
-    std::vector<float> tmp(n);
-    for (size_t i = 0; i < n; ++i) tmp[i] = host[2 * i];   // value lives in .x (inc/cupss/field.h:67)
-    CK(cudaMemcpyAsync(p->realBuf, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->viewBuf, host, n * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+    CK(launch_real_compress(p->viewBuf, p->realBuf, n, p->stream));
     CKR(p->forward_full(F.S));
     CK(cudaStreamSynchronize(p->stream));
     return CUPSS_B200_OK;
@@ -1231,12 +1238,12 @@ int cupss_b200_download_real(cupss_b200_plan* p, int f, float* host) {
     Field& F = p->fields[f];
     if (!F.S || !host) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
     CKR(ensure_real_buf(p));
+    CKR(ensure_view_buf(p));
     CKR(p->inverse_full(F.S));
     const size_t n = (size_t)p->sx * p->sy * p->zl;
-    std::vector<float> tmp(n);
-    CK(cudaMemcpyAsync(tmp.data(), p->realBuf, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(launch_real_expand(p->realBuf, p->viewBuf, n, p->stream));
+    CK(cudaMemcpyAsync(host, p->viewBuf, n * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    for (size_t i = 0; i < n; ++i) { host[2 * i] = tmp[i]; host[2 * i + 1] = 0.0f; }
     return CUPSS_B200_OK;
 }
 
@@ -1245,23 +1252,11 @@ int cupss_b200_download_comp(cupss_b200_plan* p, int f, float* host) {
     Field& F = p->fields[f];
     if (!F.S || !host) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
     if (p->nranks != 1) return fail(CUPSS_B200_ERR_ARG, "download_comp is single-rank only");
-    std::vector<float2> half(p->specElems);
-    CK(cudaMemcpyAsync(half.data(), F.S, p->specElems * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+    CKR(ensure_view_buf(p));
+    const size_t n = (size_t)p->sx * p->sy * p->sz;
+    CK(launch_spectrum_expand(F.S, p->viewBuf, p->sx, p->sy, p->sz, p->pitch, p->stream));
+    CK(cudaMemcpyAsync(host, p->viewBuf, n * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    const int sx = p->sx, sy = p->sy, sz = p->sz, pitch = p->pitch;
-    for (int k = 0; k < sz; ++k)
-        for (int j = 0; j < sy; ++j)
-            for (int i = 0; i < sx; ++i) {
-                float2 v;
-                if (i <= sx / 2) v = half[((size_t)k * sy + j) * pitch + i];
-                else {
-                    const int mk = (sz - k) % sz, mj = (sy - j) % sy;
-                    v = half[((size_t)mk * sy + mj) * pitch + (sx - i)];
-                    v.y = -v.y;
-                }
-                const size_t o = ((size_t)k * sy + j) * sx + i;
-                host[2 * o] = v.x; host[2 * o + 1] = v.y;
-            }
     return CUPSS_B200_OK;
 }
 

@@ -101,6 +101,8 @@ cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
 // float <-> float2 views of a real field (user callbacks see float2[N] with the value in .x, like the reference)
 cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStream_t st);
 cudaError_t launch_real_compress(const float2* in, float* out, size_t n, cudaStream_t st);
+// Hermitian half spectrum [sz][sy][pitch] -> full spectrum float2[sz][sy][sx] (comp_array layout of the reference)
+cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, cudaStream_t st);
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
 // Level twiddle table of an L-point transform (fft_core.cuh); returns the number of entries written (<= L), 0 if unsupported.

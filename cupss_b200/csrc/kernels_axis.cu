@@ -551,6 +551,27 @@ __global__ void real_expand_kernel(const float* __restrict__ in, float2* __restr
 __global__ void real_compress_kernel(const float2* __restrict__ in, float* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i].x;
 }
+__global__ void spectrum_expand_kernel(const float2* __restrict__ half, float2* __restrict__ full, int sx, int sy, int sz, int pitch) {
+    const size_t n = (size_t)sx * sy * sz;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(o % sx);
+        const size_t r = o / sx;
+        const int j = (int)(r % sy), k = (int)(r / sy);
+        float2 v;
+        if (i <= sx / 2) {
+            v = half[((size_t)k * sy + j) * pitch + i];
+        } else {   // X(k) = conj X(-k)
+            const int mk = (sz - k) % sz, mj = (sy - j) % sy;
+            v = half[((size_t)mk * sy + mj) * pitch + (sx - i)];
+            v.y = -v.y;
+        }
+        full[o] = v;
+    }
+}
+cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, cudaStream_t st) {
+    spectrum_expand_kernel<<<148 * 8, 256, 0, st>>>(half, full, sx, sy, sz, pitch);
+    return cudaGetLastError();
+}
 cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStream_t st) {
     real_expand_kernel<<<148 * 8, 256, 0, st>>>(in, out, n);
     return cudaGetLastError();

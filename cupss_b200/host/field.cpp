@@ -4,30 +4,48 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../inc/cupss.h"
 
 static float q_step(float d, int n) { return 2.0f * PI / (d * (float)n); }
 
+// Host mirrors (float2[N], value in .x, as in the reference).  Page-locked when a CUDA device is present so that the
+// upload / download copies run at full PCIe speed; plain memory otherwise (a GPU-less host can still declare a system).
+static float2 *alloc_mirror(size_t n, bool *pinned) {
+    void *p = nullptr;
+    *pinned = false;
+    if (n * sizeof(float2) >= (1u << 20) && cudaHostAlloc(&p, n * sizeof(float2), cudaHostAllocDefault) == cudaSuccess) {
+        *pinned = true;
+        memset(p, 0, n * sizeof(float2));
+        return static_cast<float2 *>(p);
+    }
+    (void)cudaGetLastError();
+    return new float2[n]();
+}
+static void free_mirror(float2 *p, bool pinned) {
+    if (pinned) cudaFreeHost(p); else delete[] p;
+}
+
 field::field(int nx, float hx)
     : sx(nx), sy(1), sz(1), dx(hx), dy(1.0f), dz(1.0f), stepqx(q_step(hx, nx)), stepqy(2.0f * PI), stepqz(2.0f * PI) {
-    real_array = new float2[(size_t)sx * sy * sz]();
-    comp_array = new float2[(size_t)sx * sy * sz]();
+    real_array = alloc_mirror((size_t)sx * sy * sz, &real_pinned);
+    comp_array = alloc_mirror((size_t)sx * sy * sz, &comp_pinned);
 }
 field::field(int nx, int ny, float hx, float hy)
     : sx(nx), sy(ny), sz(1), dx(hx), dy(hy), dz(1.0f), stepqx(q_step(hx, nx)), stepqy(q_step(hy, ny)), stepqz(2.0f * PI) {
-    real_array = new float2[(size_t)sx * sy * sz]();
-    comp_array = new float2[(size_t)sx * sy * sz]();
+    real_array = alloc_mirror((size_t)sx * sy * sz, &real_pinned);
+    comp_array = alloc_mirror((size_t)sx * sy * sz, &comp_pinned);
 }
 field::field(int nx, int ny, int nz, float hx, float hy, float hz)
     : sx(nx), sy(ny), sz(nz), dx(hx), dy(hy), dz(hz), stepqx(q_step(hx, nx)), stepqy(q_step(hy, ny)), stepqz(q_step(hz, nz)) {
-    real_array = new float2[(size_t)sx * sy * sz]();
-    comp_array = new float2[(size_t)sx * sy * sz]();
+    real_array = alloc_mirror((size_t)sx * sy * sz, &real_pinned);
+    comp_array = alloc_mirror((size_t)sx * sy * sz, &comp_pinned);
 }
 
 field::~field() {
-    delete[] real_array;
-    delete[] comp_array;
+    free_mirror(real_array, real_pinned);
+    free_mirror(comp_array, comp_pinned);
     for (term *t : terms) delete t;
 }
 

@@ -74,6 +74,7 @@ class field {
     const float dx, dy, dz;
     const float stepqx, stepqy, stepqz;
     std::vector<std::string> implicit_prefactor_strings;
+    bool real_pinned = false, comp_pinned = false;   // host mirrors are page-locked when a device is present
 };
 
 #endif

@@ -79,7 +79,11 @@ def test_parity_with_compiled_reference(built, name):
 def test_reference_gpu_path_agrees_with_oracle_f_and_product(built, name):
     """ORACLE-F (CPU sources + two one-token fixes) is meant to reproduce the semantics of the reference's GPU
     kernels.  Here the reference's OWN cuFFT/cuRAND build (unmodified sources, oracle/_ref/libcupss_ref_gpu.so) runs on the
-    same input: it must agree with ORACLE-F, and the product must agree with it."""
+    same input as a third witness.  The reference's two paths do not agree with EACH OTHER to the 1e-5 of the north star
+    (measured: 5.4e-5 on ch3d_32 after 100 steps -- FMA contraction and cuFFT vs FFTW-order rounding, amplified by the
+    linearly unstable dynamics), so this is a loose check (3e-4) that the one-token fixes of ORACLE-F reproduce the GPU
+    kernels' semantics -- a wrong dealias mask or a wrong constraint-field denominator shows up at 1e-2.
+    The binding parity gate is the CPU path (test_parity_with_compiled_reference)."""
     if not os.path.exists(cases.REF_GPU):
         pytest.skip("oracle/_ref/libcupss_ref_gpu.so not built")
     case = CASES[name]
@@ -87,8 +91,7 @@ def test_reference_gpu_path_agrees_with_oracle_f_and_product(built, name):
     ref_cpu = cases.run_case(case, lib=ORACLE_F, device=0)
     got = cases.run_case(case)
     for f, _ in case["fields"]:
-        # small-norm derived fields of Model H sit on the reference's own float32 cancellation floor
-        tol = 5e-5 if name == "modelh_32" and f in ("w", "vx", "vy", "P") else 2e-5
+        tol = 3e-4
         assert rel_l2(ref_cpu[f], ref_gpu[f]) < tol, ("oracle-F vs reference GPU", f, rel_l2(ref_cpu[f], ref_gpu[f]))
         assert rel_l2(got[f], ref_gpu[f]) < tol, ("product vs reference GPU", f, rel_l2(got[f], ref_gpu[f]))
 
