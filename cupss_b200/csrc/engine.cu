@@ -98,6 +98,137 @@ static int load_nccl() {
         if (r_ != 0) return fail(CUPSS_B200_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
     } while (0)
 
+// ---------------------------------------------------------------- run-time compilation of plan-specialised k stages
+// A generic sweep (anything outside the q^2-polynomial class) is evaluated by an interpreter over the plan descriptors
+// (kstage_point).  For grids where it matters the STRUCTURE of the sweep -- counts, source / destination indices, exponents,
+// flags -- is turned into a constexpr plan type and the k-stage kernel is compiled for it with NVRTC from the very same
+// headers (kernels_axis.cuh): every descriptor read, loop and branch of the interpreter folds away.  Coefficients, cut-offs
+// and noise amplitudes stay run-time arguments, so updateParameter re-uses the compiled kernel.  NVRTC and the driver API
+// are bound lazily; if either is missing the interpreter runs instead (same results).
+namespace {
+struct JitApi {
+    bool tried = false, ok = false;
+    void *hn = nullptr, *hc = nullptr;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    int (*ModuleLoadData)(void**, const void*) = nullptr;
+    int (*ModuleGetFunction)(void**, void*, const char*) = nullptr;
+    int (*FuncSetAttribute)(void*, int, int) = nullptr;
+    int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, cudaStream_t, void**, void**) = nullptr;
+    std::map<std::string, void*> cache;   // source -> CUfunction
+    std::string csrcDir;
+};
+}  // namespace
+static JitApi g_jit;
+
+static bool jit_load() {
+    if (g_jit.tried) return g_jit.ok;
+    g_jit.tried = true;
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so"}) { g_jit.hn = dlopen(n, RTLD_NOW); if (g_jit.hn) break; }
+    for (const char* n : {"libcuda.so.1", "libcuda.so"}) { g_jit.hc = dlopen(n, RTLD_NOW); if (g_jit.hc) break; }
+    if (!g_jit.hn || !g_jit.hc) return false;
+#define JSYM(h, field, name) *(void**)(&g_jit.field) = dlsym(g_jit.h, name); if (!g_jit.field) return false;
+    JSYM(hn, CreateProgram, "nvrtcCreateProgram") JSYM(hn, CompileProgram, "nvrtcCompileProgram")
+    JSYM(hn, GetProgramLogSize, "nvrtcGetProgramLogSize") JSYM(hn, GetProgramLog, "nvrtcGetProgramLog")
+    JSYM(hn, GetCUBINSize, "nvrtcGetCUBINSize") JSYM(hn, GetCUBIN, "nvrtcGetCUBIN") JSYM(hn, DestroyProgram, "nvrtcDestroyProgram")
+    JSYM(hc, ModuleLoadData, "cuModuleLoadData") JSYM(hc, ModuleGetFunction, "cuModuleGetFunction")
+    JSYM(hc, FuncSetAttribute, "cuFuncSetAttribute") JSYM(hc, LaunchKernel, "cuLaunchKernel")
+#undef JSYM
+    Dl_info info;
+    if (!dladdr((void*)&jit_load, &info) || !info.dli_fname) return false;
+    std::string lib = info.dli_fname;                       // .../cupss_b200/lib/libcupss_b200.so
+    const size_t slash = lib.find_last_of('/');
+    g_jit.csrcDir = (slash == std::string::npos ? std::string(".") : lib.substr(0, slash)) + "/../csrc";
+    FILE* f = fopen((g_jit.csrcDir + "/kernels_axis.cuh").c_str(), "r");
+    if (!f) return false;
+    fclose(f);
+    g_jit.ok = true;
+    return true;
+}
+
+// constexpr plan type + entry point for one sweep
+static std::string jit_source(const cupss::KStageD& ks, int L) {
+    using namespace cupss;
+    std::string s = "#include \"kernels_axis.cuh\"\nnamespace cupss {\nstruct JitPlan {\n";
+    char b[256];
+    int npres = 0, nterm = 0;
+    for (int o = 0; o < ks.nout; ++o) {
+        nterm = std::max(nterm, ks.out[o].termOff + ks.out[o].nterm);
+        npres = std::max(npres, ks.out[o].impOff + ks.out[o].nimp);
+    }
+    for (int t = 0; t < nterm; ++t) npres = std::max(npres, ks.term[t].presOff + ks.term[t].npres);
+    snprintf(b, sizeof b, "    static constexpr int nsrc = %d, nout = %d;\n", ks.nsrc, ks.nout);
+    s += b;
+    s += "    CUPSS_HD static constexpr PlanOut out(int o) {\n        switch (o) {\n";
+    for (int o = 0; o < ks.nout; ++o) {
+        const OutD& d = ks.out[o];
+        snprintf(b, sizeof b, "            case %d: return PlanOut{%d, %d, %d, %d, %d, %d, %d, %d, %d};\n", o, d.termOff, d.impOff, d.nterm, d.nimp,
+                 d.dynamic, d.noisy, d.selfSrc, d.dst, d.inv);
+        s += b;
+    }
+    s += "        }\n        return PlanOut{};\n    }\n    CUPSS_HD static constexpr PlanTerm term(int t) {\n        switch (t) {\n";
+    for (int t = 0; t < nterm; ++t) {
+        const TermD& d = ks.term[t];
+        snprintf(b, sizeof b, "            case %d: return PlanTerm{%d, %d, %d, %d};\n", t, d.presOff, d.npres, d.src, d.mulI);
+        s += b;
+    }
+    s += "        }\n        return PlanTerm{};\n    }\n    CUPSS_HD static constexpr PlanPres pres(int i) {\n        switch (i) {\n";
+    for (int i = 0; i < npres; ++i) {
+        const PresD& d = ks.pres[i];
+        snprintf(b, sizeof b, "            case %d: return PlanPres{%d, %d, %d, %d, %d};\n", i, d.q2n, d.iqx, d.iqy, d.iqz, d.invq);
+        s += b;
+    }
+    s += "        }\n        return PlanPres{};\n    }\n};\n}  // namespace cupss\n";
+    snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(cupss::AxisCfg<%d>::THREADS, cupss::AxisCfg<%d>::MINB)\n", L, L);
+    s += b;
+    s += "jit_kstage(const __grid_constant__ cupss::AxisArgs a, const __grid_constant__ cupss::KStageD ks) {\n";
+    snprintf(b, sizeof b, "    cupss::axis_kstage_body<%d, cupss::KS_JIT, -1, cupss::JitPlan>(a, ks);\n}\n", L);
+    s += b;
+    return s;
+}
+
+// Returns the CUfunction of the specialised kernel, or nullptr (with the reason in `why`) if it cannot be built.
+static void* jit_kstage_function(const cupss::KStageD& ks, int L, std::string* why) {
+    if (!jit_load()) { *why = "NVRTC / driver API / kernel sources not available"; return nullptr; }
+    const std::string src = jit_source(ks, L);
+    auto it = g_jit.cache.find(src);
+    if (it != g_jit.cache.end()) return it->second;
+    void* prog = nullptr;
+    if (g_jit.CreateProgram(&prog, src.c_str(), "cupss_b200_jit_kstage.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return nullptr; }
+    const std::string inc1 = "-I" + g_jit.csrcDir;
+    const char* cudaHome = getenv("CUDA_HOME");
+    const std::string inc2 = std::string("-I") + (cudaHome ? cudaHome : "/usr/local/cuda") + "/include";
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", inc1.c_str(), inc2.c_str()};
+    const int rc = g_jit.CompileProgram(prog, 5, opts);
+    if (rc != 0) {
+        size_t n = 0;
+        g_jit.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_jit.GetProgramLog(prog, &log[0]);
+        *why = "nvrtcCompileProgram failed: " + log.substr(0, 600);
+        g_jit.DestroyProgram(&prog);
+        return nullptr;
+    }
+    size_t n = 0;
+    g_jit.GetCUBINSize(prog, &n);
+    std::vector<char> cubin(n);
+    g_jit.GetCUBIN(prog, cubin.data());
+    g_jit.DestroyProgram(&prog);
+    void *mod = nullptr, *fn = nullptr;
+    if (g_jit.ModuleLoadData(&mod, cubin.data()) != 0 || g_jit.ModuleGetFunction(&fn, mod, "jit_kstage") != 0) { *why = "cuModuleLoadData failed"; return nullptr; }
+    int threads = 0, minb = 0;
+    size_t smem = 0;
+    axis_kstage_geometry(L, &threads, &smem, &minb);
+    if (smem > 48 * 1024 && g_jit.FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8, (int)smem) != 0) { *why = "cuFuncSetAttribute failed"; return nullptr; }
+    g_jit.cache[src] = fn;
+    return fn;
+}
+
 // ---------------------------------------------------------------- plan data model
 namespace {
 
@@ -135,9 +266,11 @@ struct Launch {
     // Two-lane schedule: lane 1 runs on a side stream (a parallel branch of the CUDA graph) so that the NVLink-bound
     // pushed y pass of chunk c overlaps the x pass of chunk c+1.  waitEv / sigEv: event waited on before / recorded after.
     int lane = 0, waitEv = -1, sigEv = -1;
+    void* jitFn = nullptr;   // plan-specialised k stage compiled at run time (AXIS_KSTAGE), else the library's kernels
 };
 
 int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+int FftLevelsN(int L) { return L <= 16 ? 1 : 2; }   // only "more than one level" matters here (the tile exists)
 
 }  // namespace
 
@@ -352,7 +485,19 @@ struct cupss_b200_plan {
         switch (l.kind) {
             case Launch::XPASS: CK(launch_xpass(sx, l.mode, l.xa, stream)); break;
             case Launch::AXIS_PLAIN: CK(launch_axis_plain(l.L, l.dir, l.ax, stream)); break;
-            case Launch::AXIS_KSTAGE: CK(launch_axis_kstage(l.L, l.ax, l.ks, stream)); break;
+            case Launch::AXIS_KSTAGE:
+                if (l.jitFn) {
+                    int threads = 0, minb = 0;
+                    size_t smem = 0;
+                    axis_kstage_geometry(l.L, &threads, &smem, &minb);
+                    void* params[] = {&l.ax, &l.ks};
+                    const unsigned grid = (unsigned)l.ax.ncolTiles * (unsigned)l.ax.nbatch;
+                    const int rc = g_jit.LaunchKernel(l.jitFn, grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, stream, params, nullptr);
+                    if (rc != 0) return fail(CUPSS_B200_ERR_CUDA, "cuLaunchKernel of the plan-specialised k stage failed (%d)", rc);
+                } else {
+                    CK(launch_axis_kstage(l.L, l.ax, l.ks, stream));
+                }
+                break;
             case Launch::BUMP: CK(launch_bump_counter(stepCounter, stream)); break;
             case Launch::XBAR: CK(launch_xgpu_barrier(l.xb, stream)); break;
             case Launch::A2A: {
@@ -799,6 +944,17 @@ struct cupss_b200_plan {
                 q.nimp = ks.out[0].nimp;
                 for (int i = 0; i < q.nimp; ++i) { q.ipre[i] = (double)ks.pres[ks.out[0].impOff + i].pre; q.in[i] = ks.pres[ks.out[0].impOff + i].q2n; }
                 ks.fastKind = KS_SCALAR_Q2;
+            }
+        }
+        if (ks.fastKind == KS_GENERIC) {
+            // plan-specialised kernel for grids where the interpreter's overhead matters (or on request)
+            const char* je = getenv("CUPSS_B200_JIT");
+            const bool force = je && je[0] == '1', off = je && je[0] == '0';
+            const double points = (double)sx * sy * sz;
+            if (!off && (force || points >= (double)(1 << 18)) && FftLevelsN(k.L) > 1) {
+                std::string why;
+                k.jitFn = jit_kstage_function(ks, k.L, &why);
+                if (!k.jitFn && (force || getenv("CUPSS_B200_VERBOSE"))) fprintf(stderr, "cupss_b200: k stage not specialised (%s); using the interpreter\n", why.c_str());
             }
         }
         float2* invOut = nullptr;

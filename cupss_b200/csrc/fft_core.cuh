@@ -28,8 +28,15 @@
 // Everything is __host__ __device__: tests/host/fft_core_check.cu runs the very same level arithmetic
 // on the CPU (there is no GPU in the build container).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (plan-specialised k stage, engine.cu): no host headers
+#include <cuda/std/utility>
+namespace cupss_std = cuda::std;
+#else
 #include <cuda_runtime.h>
 #include <utility>
+namespace cupss_std = std;
+#endif
 
 #define CUPSS_HD __host__ __device__ __forceinline__
 
@@ -120,7 +127,7 @@ struct Dft {
     }
     template <int... K>
     static CUPSS_HD void combine(float2 (&x)[N], const float2 (&e)[N / 2], const float2 (&o)[N / 2],
-                                 std::integer_sequence<int, K...>) {
+                                 cupss_std::integer_sequence<int, K...>) {
         (comb1<K>(x, e, o), ...);
     }
     static CUPSS_HD void run(float2 (&x)[N]) {
@@ -129,7 +136,7 @@ struct Dft {
         for (int i = 0; i < N / 2; ++i) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
         Dft<N / 2, DIR>::run(e);
         Dft<N / 2, DIR>::run(o);
-        combine(x, e, o, std::make_integer_sequence<int, N / 2>{});
+        combine(x, e, o, cupss_std::make_integer_sequence<int, N / 2>{});
     }
 };
 template <int DIR>
@@ -208,6 +215,7 @@ CUPSS_HD unsigned freq_of_pos(unsigned p) {
     return k;
 }
 
+#ifndef __CUDACC_RTC__
 // Host: fill the level twiddle table of L (TwTable<L>::LEN entries).
 template <int L, int LV>
 inline void fill_level_twiddles(float2* out) {
@@ -224,6 +232,7 @@ inline void fill_level_twiddles(float2* out) {
         fill_level_twiddles<L, LV + 1>(out);
     }
 }
+#endif
 
 // Position that holds frequency k after the forward transform (inverse map of freq_of_pos).
 template <int L>

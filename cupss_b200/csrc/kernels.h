@@ -1,6 +1,8 @@
 // kernels.h -- host-visible launch interface of the sm_100a step kernels (internal to the engine).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include "kstage.cuh"
 
 namespace cupss {
@@ -92,6 +94,7 @@ struct XArgs {
 
 enum XMode { X_HOT = 0, X_C2R_ONLY = 1, X_R2C_ONLY = 2 };
 
+#ifndef __CUDACC_RTC__
 // Launchers return cudaError_t of the launch; unsupported sizes return cudaErrorInvalidValue.
 cudaError_t launch_axis_plain(int L, int dir, const AxisArgs& a, cudaStream_t st);
 cudaError_t launch_axis_kstage(int L, const AxisArgs& a, const KStageD& ks, cudaStream_t st);
@@ -105,6 +108,8 @@ cudaError_t launch_real_compress(const float2* in, float* out, size_t n, cudaStr
 cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, cudaStream_t st);
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
+// Launch geometry of the k-stage kernel for length L (for kernels compiled at run time)
+bool axis_kstage_geometry(int L, int* threads, size_t* smem, int* minBlocks);
 // Level twiddle table of an L-point transform (fft_core.cuh); returns the number of entries written (<= L), 0 if unsupported.
 int host_level_twiddles(int L, float2* out);
 // Two-level x pass (kernels_x3.cu): sizes it covers, its twiddle table (<= sx entries) and its launcher.
@@ -112,5 +117,7 @@ bool xpass3_supported(int sx);
 int host_x3_twiddles(int sx, float2* out);
 cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st);
 bool fft_size_supported(int n);
+
+#endif
 
 }  // namespace cupss

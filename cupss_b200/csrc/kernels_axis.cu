@@ -13,392 +13,9 @@
 // The second is the heart of the step: the last level of the forward transform of the nonlinear term, the
 // semi-implicit Euler update, the dealiasing mask and the first level of the next inverse transform happen
 // on the same registers; the data never leaves the SM between the two transforms.
-#include "kernels.h"
+#include "kernels_axis.cuh"
 
 namespace cupss {
-
-template <int L> struct AxisCfg {
-    static constexpr int C = L <= 512 ? 16 : (L <= 2048 ? 8 : (L <= 4096 ? 4 : 2));
-    static constexpr int CP = C / 2;                                   // float4 column pairs
-    static constexpr int NVMAX = L / FftLevels<L>::min_rad();          // most virtual threads any level has
-    static constexpr size_t TILE = (size_t)L * CP * sizeof(float4);
-    static constexpr size_t SMEM = (FftLevels<L>::n > 1 ? TILE : 0) + (size_t)TwTable<L>::LEN * sizeof(float2);
-    static constexpr int WANT = CP * NVMAX;
-    static constexpr int TMAX = SMEM > 100 * 1024 ? 512 : 256;
-    static constexpr int THREADS = WANT < 32 ? 32 : (WANT > TMAX ? TMAX : WANT);
-    static constexpr int TV = THREADS / CP;
-    static constexpr int MINB = THREADS >= 512 ? 1 : (SMEM > 100 * 1024 ? 1 : (SMEM > 70 * 1024 ? 2 : 3));
-};
-
-// Element offset of (batch b, row, column col).  32-bit arithmetic: the engine refuses arrays of 2^31 elements or more.
-__device__ __forceinline__ unsigned axis_off(const AxisAddr& a, unsigned b, unsigned row, unsigned col) {
-    return b * (unsigned)a.bs + (row >> a.rpcShift) * (unsigned)a.cs + (row & (unsigned)a.rpcMask) * (unsigned)a.rs + col;
-}
-// Same with the row-independent part (b * bs + col) hoisted by the caller.
-__device__ __forceinline__ unsigned row_off(const AxisAddr& a, unsigned row) {
-    return (row >> a.rpcShift) * (unsigned)a.cs + (row & (unsigned)a.rpcMask) * (unsigned)a.rs;
-}
-
-// Destination of row `row`: local array, or the receive buffer of the peer that owns the row (fused slab exchange).
-// `lbase` = out + b*bs + col (local), `pbase` = pushBase + b*pushBs + col (element offset inside every peer's arena).
-__device__ __forceinline__ float2* axis_dst(const AxisArgs& a, float2* lbase, unsigned long long pbase, unsigned row) {
-    if (a.pushOn)
-        return a.push[row >> a.pushShift] + pbase + (unsigned long long)((row & (unsigned)a.pushMask)) * (unsigned long long)a.pushRs;
-    return lbase + row_off(a.aout, row);
-}
-
-__device__ __forceinline__ float4 ld4(const float2* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void st4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-
-// ---------------------------------------------------------------- exchange synchronisation folded into the kernels
-// Consumer side: called by every CTA before it touches a receive slot.
-__device__ __forceinline__ void exchange_wait(const AxisArgs& a) {
-    if (!a.waitOn) return;
-    if (threadIdx.x == 0) {
-        unsigned int* hdr = reinterpret_cast<unsigned int*>(a.push[a.rank]);
-        const unsigned int target = *reinterpret_cast<volatile unsigned int*>(hdr + XH_EPOCH + a.waitPt);   // bumped by this GPU's own producer (stream order)
-        const long long t0 = clock64();
-        for (int d = 0; d < a.nranks; ++d) {
-            const unsigned int* f = hdr + XH_FLAGS + a.waitPt * CUPSS_MAX_PEERS + d;
-            unsigned int seen;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-                if (clock64() - t0 > 6000000000LL) { *reinterpret_cast<int*>(hdr + XH_ERROR) = 1; break; }   // ~3 s: a peer died; do not hang the GPU
-            } while ((int)(seen - target) < 0);
-        }
-    }
-    __syncthreads();
-}
-// Producer side: called by every CTA (also the ones that exit early) after its last store to a peer.
-__device__ __forceinline__ void exchange_signal(const AxisArgs& a) {
-    if (!a.sigOn) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int* hdr = reinterpret_cast<unsigned int*>(a.push[a.rank]);
-        __threadfence_system();                                   // this CTA's peer stores before the count
-        const unsigned int prev = atomicAdd(hdr + XH_DONE + a.sigPt, 1u);
-        if (prev + 1u == a.sigTotal) {                            // last CTA of the last chunk launch
-            __threadfence_system();                               // every other CTA's stores (fence-atomic-fence chain)
-            hdr[XH_DONE + a.sigPt] = 0u;
-            const unsigned int target = hdr[XH_EPOCH + a.sigPt] + 1u;
-            hdr[XH_EPOCH + a.sigPt] = target;
-            for (int d = 0; d < a.nranks; ++d) {
-                unsigned int* theirs = reinterpret_cast<unsigned int*>(a.push[d]) + XH_FLAGS + a.sigPt * CUPSS_MAX_PEERS + a.rank;
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(target) : "memory");
-            }
-        }
-    }
-}
-
-// 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed): the whole input tile of a CTA is put in flight by
-// its first few instructions, with no register staging, so the HBM latency is paid once per tile and overlaps the
-// arithmetic of the other CTAs resident on the SM.
-__device__ __forceinline__ void cp_async16(float4* smemDst, const float2* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smemDst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-// Tile prologue: position p of the tile <- row rowOf(p) of the input (natural order for a forward transform, frequency
-// order for an inverse one).  Rows that are known zeros (keep(row) false) and invalid column pairs are zero-filled.
-template <int L, int CP, int TV, class RowOf, class Keep>
-__device__ __forceinline__ void tile_fetch(float4* tile, unsigned tv, unsigned cp, bool valid, const float2* ibase, const AxisAddr& ain,
-                                           RowOf rowOf, Keep keep) {
-#pragma unroll 4
-    for (unsigned p = tv; p < (unsigned)L; p += TV) {
-        const unsigned row = rowOf(p);
-        float4* dst = tile + p * CP + cp;
-        if (valid && keep(row)) cp_async16(dst, ibase + row_off(ain, row));
-        else *dst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-}
-
-// One level over the tile: every real thread walks its virtual threads (v = tv, tv + TV, ...).
-//   ld(pos, frow) -> float4, st(pos, frow, value);  pos = position inside the tile, frow = frequency row that
-//   position holds in the digit-reversed order (only meaningful on the innermost level, M == 1).
-template <int L, int LV, int DIR, int TV, class LdF, class StF>
-__device__ __forceinline__ void tile_level(unsigned tv, const float2* __restrict__ twS, LdF ld, StF st) {
-    using G = LevelGeom<L, LV>;
-    constexpr unsigned R = G::R, M = G::M, N = G::N;
-#pragma unroll 1
-    for (unsigned v = tv; v < (unsigned)G::NV; v += TV) {
-        const unsigned blk = v / M, j = v % M;
-        const unsigned row0 = blk * N + j;
-        const unsigned f0 = M == 1 ? freq_of_pos<L>(v * R) : 0u;
-        float2 x0[R], x1[R];
-#pragma unroll
-        for (unsigned q = 0; q < R; ++q) {
-            const float4 t = ld(row0 + M * q, f0 + (L / R) * q);
-            x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
-        }
-        level_butterfly2<L, LV, DIR, (DIR < 0)>(x0, x1, j, twS);
-#pragma unroll
-        for (unsigned q = 0; q < R; ++q) st(row0 + M * q, f0 + (L / R) * q, make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y));
-    }
-}
-
-// MASK: apply the full dealias mask on load (extra inverse transforms of a sweep; AxisArgs::maskOn).
-template <int L, int DIR, bool MASK>
-__global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_plain_kernel(const __grid_constant__ AxisArgs a) {
-    using Cfg = AxisCfg<L>;
-    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, n = FftLevels<L>::n;
-    extern __shared__ float4 smem4[];
-    float4* tile = smem4;
-    float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
-    const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
-    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles, b = blockIdx.x / (unsigned)a.ncolTiles;
-    const unsigned col = ct * C + 2 * cp;
-    const bool valid = col < (unsigned)a.ncol;
-
-    if (a.pruneOn) {   // CTA-uniform: the whole tile is outside the dealias cut-off -> output stays zero
-        const int iyT = a.kyBase + (int)b;
-        const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
-        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) { exchange_signal(a); return; }
-    }
-    exchange_wait(a);
-    auto load_twiddles = [&]() {
-        for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
-    };
-
-    const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
-    float2* lbase = a.out + (b * (unsigned)a.aout.bs + col);
-    const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
-    // rows beyond rowCut (|n| > rowCut) are known zeros: not loaded.  rowCut < 0: off.
-    const unsigned keepLo = a.rowCut >= 0 ? (unsigned)a.rowCut : (unsigned)L, keepHi = a.rowCut >= 0 ? (unsigned)(L - a.rowCut) : 0u;
-
-    auto keepRow = [&](unsigned row) -> bool { return row <= keepLo || row >= keepHi; };
-    auto gload = [&](unsigned row) -> float4 {   // direct path (single-level transforms, no tile)
-        if (!(valid && keepRow(row))) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return ld4(ibase + row_off(a.ain, row));
-    };
-    auto masked = [&](float4 t, unsigned row) -> float4 {
-        if constexpr (MASK) {
-            const int iy = a.axis == 2 ? a.kyBase + (int)b : (a.axis == 1 ? (int)row : 0);
-            const int iz = a.axis == 2 ? (int)row : 0;
-            if (!dealias_keep((int)col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.x = 0.0f; t.y = 0.0f; }
-            if (!dealias_keep((int)col + 1, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.z = 0.0f; t.w = 0.0f; }
-        }
-        return t;
-    };
-    auto gstore = [&](unsigned row, float4 v) {
-        if (valid) st4(axis_dst(a, lbase, pbase, row), v);
-    };
-    auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
-    auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
-
-    if constexpr (DIR < 0) {   // forward: natural rows in, frequency rows out
-        auto gst = [&](unsigned, unsigned frow, float4 v) { gstore(frow, v); };
-        if constexpr (n == 1) {
-            auto gld = [&](unsigned pos, unsigned) -> float4 { return gload(pos); };
-            tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
-        } else {
-            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, keepRow);
-            load_twiddles();
-            cp_async_wait_all();
-            __syncthreads();
-            tile_level<L, 0, DIR, TV>(tv, twS, sld, sst);
-            __syncthreads();
-            if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
-            tile_level<L, n - 1, DIR, TV>(tv, twS, sld, gst);
-        }
-    } else {                   // inverse: frequency rows in, natural rows out
-        auto gst = [&](unsigned pos, unsigned, float4 v) { gstore(pos, v); };
-        if constexpr (n == 1) {
-            auto gld = [&](unsigned, unsigned frow) -> float4 { return masked(gload(frow), frow); };
-            tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
-        } else {
-            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return freq_of_pos<L>(p); }, keepRow);
-            load_twiddles();
-            cp_async_wait_all();
-            __syncthreads();
-            auto mld = [&](unsigned pos, unsigned frow) -> float4 { return masked(tile[pos * CP + cp], frow); };
-            tile_level<L, n - 1, DIR, TV>(tv, twS, mld, sst);
-            __syncthreads();
-            if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
-            tile_level<L, 0, DIR, TV>(tv, twS, sld, gst);
-        }
-    }
-    exchange_signal(a);
-}
-
-template <int L, int KIND, int SIG>
-__global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB)
-axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
-    using Cfg = AxisCfg<L>;
-    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, n = FftLevels<L>::n;
-    constexpr int LAST = n - 1;
-    using G = LevelGeom<L, LAST>;
-    constexpr unsigned R = G::R;
-    extern __shared__ float4 smem4[];
-    float4* tile = smem4;
-    float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
-    const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
-    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles, b = blockIdx.x / (unsigned)a.ncolTiles;
-    const unsigned col = ct * C + 2 * cp;
-    const bool valid = col < (unsigned)a.ncol, valid1 = col + 1 < (unsigned)a.ncol;
-
-    // fixed (per thread) part of the mode index: columns = kx, and ky for a z pass
-    const int iyFix = a.axis == 2 ? a.kyBase + (int)b : 0;
-    bool doInv = ks.hasInv != 0;
-    if (doInv && a.pruneOn) {   // CTA-uniform: every mode of this tile is masked out -> nothing to transform or store
-        const int nyT = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
-        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) doInv = false;
-    }
-
-    // k-space arrays (sources, destinations) share the natural addressing of the pass output: b*bs + row*rs + col
-    const unsigned kbase = b * (unsigned)a.aout.bs + col;
-    const unsigned krs = (unsigned)a.aout.rs;
-    const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
-    float2* lbase = a.out + kbase;
-    const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
-
-    exchange_wait(a);
-    if constexpr (n > 1) {
-        if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
-    }
-    for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
-    if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
-        // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
-        const float2* p0 = ks.src[0] + (b * (unsigned)a.aout.bs + ct * C);
-        for (unsigned r = threadIdx.x; r < (unsigned)L; r += Cfg::THREADS)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + r * krs));
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
-    auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
-
-    // ---- forward levels 0 .. n-2 (the last level is fused with the k stage below)
-    if (ks.hasFwd) {
-        if constexpr (n > 1) {
-            tile_level<L, 0, -1, TV>(tv, twS, sld, sst);
-            __syncthreads();
-            if constexpr (n >= 3) { tile_level<L, 1, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 4) { tile_level<L, 2, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
-        }
-    }
-
-    // ---- per-thread constants of the lean evaluator
-    const OutD& od0 = ks.out[0];
-    const int sRow = a.axis == 2 ? ks.sz : (a.axis == 1 ? ks.sy : 1);
-    const float stepRow = a.axis == 2 ? ks.stepqz : ks.stepqy;
-    const int cutRow = a.axis == 2 ? od0.cutz : od0.cuty;
-    const float qxa = wavenumber((int)col, ks.sx, ks.stepqx), qxb = wavenumber((int)col + 1, ks.sx, ks.stepqx);
-    const float qyFix = wavenumber(iyFix, ks.sy, ks.stepqy);
-    const float qxa2 = CUPSS_FMUL(qxa, qxa), qxb2 = CUPSS_FMUL(qxb, qxb);
-    const float qyFix2 = CUPSS_FMUL(qyFix, qyFix);
-    const bool fixY = (iyFix == 0) || (2 * iyFix == ks.sy);
-    const bool fixSelfA = ((col == 0) || (2 * (int)col == ks.sx)) && fixY;
-    const bool fixSelfB = (2 * ((int)col + 1) == ks.sx) && fixY;
-    const int nyFix = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
-    const bool keepY = od0.inv && (a.axis != 2 || nyFix <= od0.cuty);
-    const bool keepA = keepY && (int)col <= od0.cutx, keepB = keepY && (int)col + 1 <= od0.cutx;
-    const unsigned int step = (KIND == KS_GENERIC && ks.stepCounter) ? *ks.stepCounter : 0u;
-
-    // ---- fused level: last forward butterfly -> k stage -> first inverse butterfly
-#pragma unroll 1
-    for (unsigned v = tv; v < (unsigned)G::NV; v += TV) {
-        const unsigned f0 = freq_of_pos<L>(v * R);
-        float2 x0[R], x1[R];
-        if (ks.hasFwd) {
-#pragma unroll
-            for (unsigned q = 0; q < R; ++q) {
-                float4 t;
-                if constexpr (n > 1) t = tile[(v * R + q) * CP + cp];
-                else t = valid ? ld4(ibase + row_off(a.ain, v * R + q)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
-            }
-            level_butterfly2<L, LAST, -1, true>(x0, x1, 0, twS);
-        } else {
-#pragma unroll
-            for (unsigned q = 0; q < R; ++q) { x0[q] = make_float2(0.0f, 0.0f); x1[q] = make_float2(0.0f, 0.0f); }
-        }
-
-        if constexpr (KIND == KS_SCALAR_Q2) {
-            const unsigned rowStride = (L / R) * krs;
-            const unsigned off0 = kbase + f0 * krs;
-            const float2* sp = ks.src[0] + off0;
-            float2* dp = ks.dst[0] + off0;
-            float4 self[R];
-#pragma unroll
-            for (unsigned q = 0; q < R; ++q)
-                self[q] = valid ? __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            const double tp[3] = {ks.sq2.tpre[0], ks.sq2.tpre[1], ks.sq2.tpre[2]};
-            const double ip[4] = {ks.sq2.ipre[0], ks.sq2.ipre[1], ks.sq2.ipre[2], ks.sq2.ipre[3]};
-            const bool termFused = ks.sq2.termFused != 0;
-            const float dt = ks.dt;
-#pragma unroll
-            for (unsigned q = 0; q < R; ++q) {
-                const int row = (int)(f0 + (L / R) * q);
-                const float qr = wavenumber(row, sRow, stepRow);
-                const float qr2 = CUPSS_FMUL(qr, qr);
-                const float q2a = CUPSS_FADD(CUPSS_FADD(qxa2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
-                const float q2b = CUPSS_FADD(CUPSS_FADD(qxb2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
-                float2 va, vb;
-                if constexpr (SIG >= 0) {
-                    va = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
-                    vb = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2b, x1[q], make_float2(self[q].z, self[q].w));
-                } else {
-                    va = kstage_point_scalar_q2(ks.sq2, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
-                    vb = kstage_point_scalar_q2(ks.sq2, dt, q2b, x1[q], make_float2(self[q].z, self[q].w));
-                }
-                const bool rowSelf = (row == 0) || (2 * row == sRow);
-                if (fixSelfA && rowSelf) va.y = 0.0f;
-                if (fixSelfB && rowSelf) vb.y = 0.0f;
-                if (!valid1) vb = make_float2(0.0f, 0.0f);   // padding column of the pitch
-                if (valid) st4(dp + q * rowStride, make_float4(va.x, va.y, vb.x, vb.y));
-                const int nr = row > sRow / 2 ? sRow - row : row;
-                const bool keepR = nr <= cutRow;
-                x0[q] = (keepA && keepR) ? va : make_float2(0.0f, 0.0f);
-                x1[q] = (keepB && keepR) ? vb : make_float2(0.0f, 0.0f);
-            }
-        } else {
-#pragma unroll 1
-            for (unsigned q = 0; q < R; ++q) {
-                const int row = (int)(f0 + (L / R) * q);
-                const int iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0);
-                const int iz = a.axis == 2 ? row : 0;
-                const long long off = (long long)(kbase + (unsigned)row * krs);
-                const float2 ra = valid ? kstage_point(ks, make_kpoint(ks, (int)col, iy, iz), x0[0], off, step) : make_float2(0.0f, 0.0f);
-                const float2 rb = valid1 ? kstage_point(ks, make_kpoint(ks, (int)col + 1, iy, iz), x1[0], off + 1, step) : make_float2(0.0f, 0.0f);
-                // rotate so that the loop body only ever touches register 0 and R-1 (rolled loop, static indices)
-#pragma unroll
-                for (unsigned i = 0; i + 1 < R; ++i) { x0[i] = x0[i + 1]; x1[i] = x1[i + 1]; }
-                x0[R - 1] = ra; x1[R - 1] = rb;
-            }
-        }
-
-        if (doInv) {
-            level_butterfly2<L, LAST, +1, false>(x0, x1, 0, twS);
-#pragma unroll
-            for (unsigned q = 0; q < R; ++q) {
-                const float4 t = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
-                if constexpr (n > 1) tile[(v * R + q) * CP + cp] = t;
-                else if (valid) st4(axis_dst(a, lbase, pbase, v * R + q), t);
-            }
-        }
-    }
-
-    // ---- inverse levels n-2 .. 0
-    if constexpr (n > 1) {
-        if (doInv) {
-            auto gst = [&](unsigned pos, unsigned, float4 v) {
-                if (valid) st4(axis_dst(a, lbase, pbase, pos), v);
-            };
-            __syncthreads();
-            if constexpr (n >= 4) { tile_level<L, 2, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 3) { tile_level<L, 1, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
-            tile_level<L, 0, +1, TV>(tv, twS, sld, gst);
-        }
-    }
-    exchange_signal(a);
-}
 
 __global__ void bump_counter_kernel(unsigned int* c) { *c += 1u; }
 
@@ -530,6 +147,15 @@ int axis_tile_cols(int L) {
 }
 
 bool fft_size_supported(int n) { return axis_tile_cols(n) != 0; }
+
+bool axis_kstage_geometry(int L, int* threads, size_t* smem, int* minBlocks) {
+    switch (L) {
+#define X(N) case N: *threads = AxisCfg<N>::THREADS; *smem = AxisCfg<N>::SMEM; *minBlocks = AxisCfg<N>::MINB; return true;
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return false;
+}
 
 int host_level_twiddles(int L, float2* out) {
     switch (L) {

@@ -118,6 +118,26 @@ def test_generic_and_lean_kstage_agree_bitwise(built):
         assert np.array_equal(np.load(a), np.load(b))
 
 
+@pytest.mark.parametrize("name", ["modelh_32", "kpz3d_32_det", "bc_even_inhomogeneous_64"])
+def test_plan_specialised_kstage_matches_interpreter(built, name):
+    """Generic sweeps: the k stage compiled at run time for the plan's structure (NVRTC, CUPSS_B200_JIT=1) and the
+    interpreter over the same descriptors (CUPSS_B200_JIT=0) execute the same IEEE operation sequence."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, cases\n"
+            "out = cases.run_case(cases.CASES[%r])\n"
+            "np.savez(sys.argv[1], **out)\n") % (ROOT, os.path.join(ROOT, "tests"), name)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        a, b = os.path.join(d, "a.npz"), os.path.join(d, "b.npz")
+        ra = subprocess.run([sys.executable, "-c", code, a], cwd=ROOT, env=dict(os.environ, CUPSS_B200_JIT="1"), capture_output=True, text=True)
+        assert ra.returncode == 0, ra.stderr[-2000:]
+        assert "not specialised" not in ra.stderr, ra.stderr[-2000:]
+        subprocess.run([sys.executable, "-c", code, b], check=True, cwd=ROOT, env=dict(os.environ, CUPSS_B200_JIT="0"))
+        A, B = np.load(a), np.load(b)
+        for f in A.files:
+            assert rel_l2(A[f], B[f]) < 1e-6, (f, rel_l2(A[f], B[f]))
+
+
 def test_step0_quirk_nonlinear_term_is_skipped_on_first_step(built):
     """real_dealiased is zero until a field's first setRHS: b = 1 and b = 0 agree after one step."""
     c1 = dict(CASES["ch2d_64"])
