@@ -29,8 +29,9 @@ __device__ __forceinline__ unsigned xpad(unsigned idx) { return idx + (idx >> 3)
 constexpr int X_THREADS = 256;
 
 // SLOTS > 0: slots per CTA known at compile time (no stash: the line buffer is the whole slot); 0: run-time (XArgs).
-template <int SX, int MODE, bool FAST, int SLOTS>
-__global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __grid_constant__ XArgs a) {
+// SUMPOW (with FAST): several inputs, every monomial a power of one input -- accumulated on registers input by input.
+template <int SX, int MODE, bool FAST, int SLOTS, bool SUMPOW = false>
+__global__ void __launch_bounds__(X_THREADS, (FAST && !SUMPOW) ? 3 : 2) xpass_kernel(const __grid_constant__ XArgs a) {
     using F = FftLevels<SX>;
     constexpr int n = F::n, LAST = n - 1, XB = XCfg<SX>::XB;
     using GL = LevelGeom<SX, LAST>;
@@ -140,6 +141,14 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
     }
 
     // ------------------------------------------------ inverse part (C2R of every input), decimation in frequency
+    // FAST with several inputs ("sum of powers": every monomial is a power of ONE input, one output): the contributions
+    // are accumulated on registers input by input, no stash.  Every thread runs the innermost loop at most once (the slot
+    // count is chosen so), so the accumulators are plain registers across the inputs.
+    float2 acc0[SUMPOW ? RL : 1], acc1[SUMPOW ? RL : 1];
+    if constexpr (SUMPOW) {
+#pragma unroll
+        for (unsigned q = 0; q < RL; ++q) { acc0[q] = make_float2(0.0f, 0.0f); acc1[q] = make_float2(0.0f, 0.0f); }
+    }
     if constexpr (MODE != X_R2C_ONLY) {
         for (int g = 0; g < a.nIn; ++g) {
             if (g > 0) __syncthreads();   // line buffers are re-used per input
@@ -208,10 +217,27 @@ __global__ void __launch_bounds__(X_THREADS, FAST ? 3 : 2) xpass_kernel(const __
                         }
                     };
                     // warp-uniform dispatch on the monomial pattern: the common single-monomial powers are straight-line code
-                    if (a.nMono == 1 && p0 == 3) apply([&](float r) { return c0 * ((r * r) * r); });
-                    else if (a.nMono == 1 && p0 == 2) apply([&](float r) { return c0 * (r * r); });
-                    else if (a.nMono == 1) apply([&](float r) { return c0 * powr(r, p0); });
-                    else apply([&](float r) { return c0 * powr(r, p0) + c1 * powr(r, p1); });
+                    if constexpr (!SUMPOW) {
+                        if (a.nMono == 1 && p0 == 3) apply([&](float r) { return c0 * ((r * r) * r); });
+                        else if (a.nMono == 1 && p0 == 2) apply([&](float r) { return c0 * (r * r); });
+                        else if (a.nMono == 1) apply([&](float r) { return c0 * powr(r, p0); });
+                        else apply([&](float r) { return c0 * powr(r, p0) + c1 * powr(r, p1); });
+                    } else {
+                        // sum of powers: add this input's monomials (in monomial order, like the stash path) to the accumulators
+                        for (int m = 0; m < a.nMono; ++m) {
+                            if (a.mono[m].fac[0] != g) continue;
+                            const float cm = a.mono[m].coef;
+                            const int pm = a.mono[m].nfac;
+#pragma unroll
+                            for (unsigned q = 0; q < RL; ++q) {
+                                acc0[q].x += cm * powr(x0[q].x, pm); acc0[q].y += cm * powr(x0[q].y, pm);
+                                acc1[q].x += cm * powr(x1[q].x, pm); acc1[q].y += cm * powr(x1[q].y, pm);
+                            }
+                        }
+                        if (g + 1 < a.nIn) continue;   // more inputs to come: nothing to transform yet
+#pragma unroll
+                        for (unsigned q = 0; q < RL; ++q) { x0[q] = acc0[q]; x1[q] = acc1[q]; }
+                    }
                     level_butterfly2<SX, LAST, -1, false>(x0, x1, 0, twS);
 #pragma unroll
                     for (unsigned q = 0; q < RL; ++q) xb[xpad(v * RL + q)] = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
@@ -321,7 +347,7 @@ template <int SX> struct XSlots {   // one virtual thread per real thread on the
     static constexpr int V = RAW < 1 ? 1 : (RAW > 64 ? 64 : RAW);
 };
 
-template <int SX, int MODE, bool FAST>
+template <int SX, int MODE, bool FAST, bool SUMPOW = false>
 static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
     constexpr int XB = XCfg<SX>::XB;
     constexpr bool STASH = (MODE == X_HOT && !FAST);
@@ -342,7 +368,7 @@ static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(xpass_kernel<SX, MODE, FAST, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(xpass_kernel<SX, MODE, FAST, CT, SUMPOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = smem;
     }
@@ -350,7 +376,7 @@ static cudaError_t launch_x(XArgs& a, cudaStream_t st) {
     a.perJobFloat2 = perSlot;
     const long long nslots = (a.nlines + 3) / 4;
     const unsigned grid = (unsigned)((nslots + slots - 1) / slots);
-    xpass_kernel<SX, MODE, FAST, CT><<<grid, threads, smem, st>>>(a);
+    xpass_kernel<SX, MODE, FAST, CT, SUMPOW><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -358,9 +384,15 @@ template <int SX>
 static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
     if (mode == X_C2R_ONLY) return launch_x<SX, X_C2R_ONLY, true>(a, st);
     if (mode == X_R2C_ONLY) return launch_x<SX, X_R2C_ONLY, true>(a, st);
-    bool fast = a.nIn == 1 && a.nOut == 1 && a.nMono >= 1 && a.nMono <= 2;
-    for (int m = 0; m < a.nMono && fast; ++m) fast = a.mono[m].nfac <= 4;
+    // FAST: one output whose monomials are powers (<= 4) of a single input each -- one input with up to two monomials, or
+    // several inputs ("sum of powers", e.g. the three squared gradients of KPZ) accumulated on registers
+    bool fast = a.nOut == 1 && a.nMono >= 1 && (a.nIn > 1 || a.nMono <= 2);
+    for (int m = 0; m < a.nMono && fast; ++m) {
+        fast = a.mono[m].nfac >= 1 && a.mono[m].nfac <= 4;
+        for (int f = 1; f < a.mono[m].nfac && fast; ++f) fast = a.mono[m].fac[f] == a.mono[m].fac[0];
+    }
     if (fast && a.tw3 && xpass3_supported(SX) && a.nMono == 1 && (a.mono[0].nfac == 2 || a.mono[0].nfac == 3)) return launch_xpass3(SX, a, st);
+    if (fast && a.nIn > 1) return launch_x<SX, X_HOT, true, true>(a, st);
     if (fast) return launch_x<SX, X_HOT, true>(a, st);
     return launch_x<SX, X_HOT, false>(a, st);
 }
