@@ -10,21 +10,29 @@
 
 static float q_step(float d, int n) { return 2.0f * PI / (d * (float)n); }
 
-// Host mirrors (float2[N], value in .x, as in the reference).  Page-locked when a CUDA device is present so that the
-// upload / download copies run at full PCIe speed; plain memory otherwise (a GPU-less host can still declare a system).
+// Host mirrors (float2[N], value in .x, as in the reference).  Page-locked when a CUDA device is present and the array is
+// at most 2 GiB, so that the upload / download copies run at full PCIe speed; larger arrays (1024^3: 8 GiB each, and every
+// rank of a partitioned run holds full-size mirrors but touches only its slab) come from calloc, i.e. untouched pages cost
+// nothing.  A GPU-less host can still declare a system.
 static float2 *alloc_mirror(size_t n, bool *pinned) {
     void *p = nullptr;
     *pinned = false;
-    if (n * sizeof(float2) >= (1u << 20) && cudaHostAlloc(&p, n * sizeof(float2), cudaHostAllocDefault) == cudaSuccess) {
+    const size_t bytes = n * sizeof(float2);
+    if (bytes >= (1u << 20) && bytes <= (2ull << 30) && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
         *pinned = true;
-        memset(p, 0, n * sizeof(float2));
+        memset(p, 0, bytes);
         return static_cast<float2 *>(p);
     }
     (void)cudaGetLastError();
-    return new float2[n]();
+    p = calloc(n, sizeof(float2));
+    if (!p) {
+        std::cout << "ERROR: cannot allocate a host mirror of " << bytes << " bytes" << std::endl;
+        std::exit(1);
+    }
+    return static_cast<float2 *>(p);
 }
 static void free_mirror(float2 *p, bool pinned) {
-    if (pinned) cudaFreeHost(p); else delete[] p;
+    if (pinned) cudaFreeHost(p); else free(p);
 }
 
 field::field(int nx, float hx)
