@@ -93,6 +93,7 @@ _ENGINE_SIGS = {
     "cupss_b200_bytes_per_step": (C.c_double, [C.c_void_p]),
     "cupss_b200_comm_bytes_per_step": (C.c_double, [C.c_void_p]),
     "cupss_b200_device_spectrum": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "cupss_b200_jit_selftest": (C.c_int, [C.c_char_p, C.c_int]),
     "cupss_b200_last_error": (C.c_char_p, []),
 }
 

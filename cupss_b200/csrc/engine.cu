@@ -107,7 +107,7 @@ static int load_nccl() {
 // are bound lazily; if either is missing the interpreter runs instead (same results).
 namespace {
 struct JitApi {
-    bool tried = false, ok = false;
+    bool tried = false, ok = false, nvrtcOk = false;   // ok: compile + load + launch; nvrtcOk: compile only
     void *hn = nullptr, *hc = nullptr;
     int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
     int (*CompileProgram)(void*, int, const char* const*) = nullptr;
@@ -131,22 +131,24 @@ static bool jit_load() {
     g_jit.tried = true;
     for (const char* n : {"libnvrtc.so.12", "libnvrtc.so"}) { g_jit.hn = dlopen(n, RTLD_NOW); if (g_jit.hn) break; }
     for (const char* n : {"libcuda.so.1", "libcuda.so"}) { g_jit.hc = dlopen(n, RTLD_NOW); if (g_jit.hc) break; }
-    if (!g_jit.hn || !g_jit.hc) return false;
+    if (!g_jit.hn) return false;
 #define JSYM(h, field, name) *(void**)(&g_jit.field) = dlsym(g_jit.h, name); if (!g_jit.field) return false;
     JSYM(hn, CreateProgram, "nvrtcCreateProgram") JSYM(hn, CompileProgram, "nvrtcCompileProgram")
     JSYM(hn, GetProgramLogSize, "nvrtcGetProgramLogSize") JSYM(hn, GetProgramLog, "nvrtcGetProgramLog")
     JSYM(hn, GetCUBINSize, "nvrtcGetCUBINSize") JSYM(hn, GetCUBIN, "nvrtcGetCUBIN") JSYM(hn, DestroyProgram, "nvrtcDestroyProgram")
-    JSYM(hc, ModuleLoadData, "cuModuleLoadData") JSYM(hc, ModuleGetFunction, "cuModuleGetFunction")
-    JSYM(hc, FuncSetAttribute, "cuFuncSetAttribute") JSYM(hc, LaunchKernel, "cuLaunchKernel")
-#undef JSYM
+    g_jit.nvrtcOk = true;
     Dl_info info;
     if (!dladdr((void*)&jit_load, &info) || !info.dli_fname) return false;
     std::string lib = info.dli_fname;                       // .../cupss_b200/lib/libcupss_b200.so
     const size_t slash = lib.find_last_of('/');
     g_jit.csrcDir = (slash == std::string::npos ? std::string(".") : lib.substr(0, slash)) + "/../csrc";
     FILE* f = fopen((g_jit.csrcDir + "/kernels_axis.cuh").c_str(), "r");
-    if (!f) return false;
+    if (!f) { g_jit.nvrtcOk = false; return false; }
     fclose(f);
+    if (!g_jit.hc) return false;   // compile-only (self test) still possible
+    JSYM(hc, ModuleLoadData, "cuModuleLoadData") JSYM(hc, ModuleGetFunction, "cuModuleGetFunction")
+    JSYM(hc, FuncSetAttribute, "cuFuncSetAttribute") JSYM(hc, LaunchKernel, "cuLaunchKernel")
+#undef JSYM
     g_jit.ok = true;
     return true;
 }
@@ -192,14 +194,30 @@ static std::string jit_source(const cupss::KStageD& ks, int L) {
     return s;
 }
 
+// NVRTC only (no driver API needed): source -> cubin.  Used by the engine and by the GPU-less self test.
+static bool jit_compile(const std::string& src, std::vector<char>* cubin, std::string* why);
+
 // Returns the CUfunction of the specialised kernel, or nullptr (with the reason in `why`) if it cannot be built.
 static void* jit_kstage_function(const cupss::KStageD& ks, int L, std::string* why) {
     if (!jit_load()) { *why = "NVRTC / driver API / kernel sources not available"; return nullptr; }
     const std::string src = jit_source(ks, L);
     auto it = g_jit.cache.find(src);
     if (it != g_jit.cache.end()) return it->second;
+    std::vector<char> cubin;
+    if (!jit_compile(src, &cubin, why)) return nullptr;
+    void *mod = nullptr, *fn = nullptr;
+    if (g_jit.ModuleLoadData(&mod, cubin.data()) != 0 || g_jit.ModuleGetFunction(&fn, mod, "jit_kstage") != 0) { *why = "cuModuleLoadData failed"; return nullptr; }
+    int threads = 0, minb = 0;
+    size_t smem = 0;
+    axis_kstage_geometry(L, &threads, &smem, &minb);
+    if (smem > 48 * 1024 && g_jit.FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8, (int)smem) != 0) { *why = "cuFuncSetAttribute failed"; return nullptr; }
+    g_jit.cache[src] = fn;
+    return fn;
+}
+
+static bool jit_compile(const std::string& src, std::vector<char>* cubin, std::string* why) {
     void* prog = nullptr;
-    if (g_jit.CreateProgram(&prog, src.c_str(), "cupss_b200_jit_kstage.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return nullptr; }
+    if (g_jit.CreateProgram(&prog, src.c_str(), "cupss_b200_jit_kstage.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return false; }
     const std::string inc1 = "-I" + g_jit.csrcDir;
     const char* cudaHome = getenv("CUDA_HOME");
     const std::string inc2 = std::string("-I") + (cudaHome ? cudaHome : "/usr/local/cuda") + "/include";
@@ -210,23 +228,16 @@ static void* jit_kstage_function(const cupss::KStageD& ks, int L, std::string* w
         g_jit.GetProgramLogSize(prog, &n);
         std::string log(n, '\0');
         if (n) g_jit.GetProgramLog(prog, &log[0]);
-        *why = "nvrtcCompileProgram failed: " + log.substr(0, 600);
+        *why = "nvrtcCompileProgram failed: " + log.substr(0, 1500);
         g_jit.DestroyProgram(&prog);
-        return nullptr;
+        return false;
     }
     size_t n = 0;
     g_jit.GetCUBINSize(prog, &n);
-    std::vector<char> cubin(n);
-    g_jit.GetCUBIN(prog, cubin.data());
+    cubin->resize(n);
+    g_jit.GetCUBIN(prog, cubin->data());
     g_jit.DestroyProgram(&prog);
-    void *mod = nullptr, *fn = nullptr;
-    if (g_jit.ModuleLoadData(&mod, cubin.data()) != 0 || g_jit.ModuleGetFunction(&fn, mod, "jit_kstage") != 0) { *why = "cuModuleLoadData failed"; return nullptr; }
-    int threads = 0, minb = 0;
-    size_t smem = 0;
-    axis_kstage_geometry(L, &threads, &smem, &minb);
-    if (smem > 48 * 1024 && g_jit.FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8, (int)smem) != 0) { *why = "cuFuncSetAttribute failed"; return nullptr; }
-    g_jit.cache[src] = fn;
-    return fn;
+    return n > 0;
 }
 
 // ---------------------------------------------------------------- plan data model
@@ -1420,6 +1431,31 @@ int cupss_b200_step(cupss_b200_plan* p, int nsteps) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
     return p->do_steps(nsteps);
 }
+int cupss_b200_jit_selftest(char* log, int loglen) {
+    // Compiles (does not load) the plan-specialised k stage of a synthetic Model-H-like sweep with NVRTC: keeps the kernel
+    // headers compilable at run time.  Works without a GPU.  Returns 0 on success, ERR_STATE if NVRTC is not installed.
+    jit_load();
+    if (!g_jit.nvrtcOk) { if (log && loglen > 0) snprintf(log, loglen, "NVRTC or the kernel sources are not available"); return fail(CUPSS_B200_ERR_STATE, "NVRTC not available"); }
+    KStageD ks{};
+    ks.nsrc = 4; ks.nout = 3; ks.hasFwd = 1; ks.hasInv = 1;
+    ks.out[0] = OutD{}; ks.out[0].termOff = 0; ks.out[0].nterm = 2; ks.out[0].impOff = 4; ks.out[0].nimp = 2; ks.out[0].dynamic = 1; ks.out[0].selfSrc = 0; ks.out[0].dst = 0; ks.out[0].inv = 1; ks.out[0].noisy = 1;
+    ks.out[1] = OutD{}; ks.out[1].termOff = 2; ks.out[1].nterm = 1; ks.out[1].impOff = 6; ks.out[1].nimp = 1; ks.out[1].selfSrc = 1; ks.out[1].dst = 1;
+    ks.out[2] = OutD{}; ks.out[2].termOff = 3; ks.out[2].nterm = 1; ks.out[2].impOff = 7; ks.out[2].nimp = 0; ks.out[2].selfSrc = 2; ks.out[2].dst = 2;
+    ks.term[0] = TermD{0, 1, -1, 0}; ks.term[1] = TermD{1, 1, 3, 1}; ks.term[2] = TermD{2, 1, 0, 1}; ks.term[3] = TermD{3, 1, 1, 0};
+    ks.pres[0].q2n = 1; ks.pres[1].iqx = 1; ks.pres[2].iqy = 1; ks.pres[2].invq = 1; ks.pres[3].iqx = 2; ks.pres[3].iqz = 1;
+    ks.pres[4].q2n = 1; ks.pres[5].q2n = 2; ks.pres[6].q2n = 1;
+    for (int L : {512, 2048, 64}) {
+        std::vector<char> cubin;
+        std::string why;
+        if (!jit_compile(jit_source(ks, L), &cubin, &why)) {
+            if (log && loglen > 0) snprintf(log, loglen, "L=%d: %s", L, why.c_str());
+            return fail(CUPSS_B200_ERR_CUDA, "plan-specialised k stage does not compile for L=%d", L);
+        }
+    }
+    if (log && loglen > 0) snprintf(log, loglen, "ok");
+    return CUPSS_B200_OK;
+}
+
 int cupss_b200_step_stage(cupss_b200_plan* p, int stage) {
     if (!p || stage < 0 || stage > 1) return fail(CUPSS_B200_ERR_ARG, "bad stage");
     return p->do_stage(stage);

@@ -104,6 +104,9 @@ double cupss_b200_bytes_per_step(cupss_b200_plan *p);   /* algorithmic HBM bytes
 double cupss_b200_comm_bytes_per_step(cupss_b200_plan *p); /* bytes this rank sends per step */
 void *cupss_b200_device_spectrum(cupss_b200_plan *p, int field);   /* borrowed device pointer (callbacks) */
 
+/* Compiles (without loading) the run-time-specialised k stage of a synthetic sweep with NVRTC; needs no GPU. */
+int cupss_b200_jit_selftest(char *log, int loglen);
+
 const char *cupss_b200_last_error(void);
 
 #ifdef __cplusplus

@@ -80,6 +80,19 @@ def test_c_abi_library_exports_every_declared_symbol(built):
     capi.load_facade(capi.PRODUCT_LIB)
 
 
+def test_plan_specialised_kstage_compiles_at_run_time(built):
+    """The generic k stage is compiled per plan with NVRTC from cupss_b200/csrc/*.cuh; the compile step needs no GPU.
+    Guards the kernel headers against constructs NVRTC cannot take (host headers, non-constexpr plan reads)."""
+    import ctypes
+    from cupss_b200 import capi
+    eng = capi.load_engine()
+    log = ctypes.create_string_buffer(4096)
+    rc = eng.cupss_b200_jit_selftest(log, len(log))
+    if rc == 3:
+        pytest.skip("NVRTC not installed: " + log.value.decode())
+    assert rc == 0, log.value.decode()
+
+
 def test_engine_kernels_are_sm100a_and_not_library_fft(built):
     from cupss_b200 import capi
     out = subprocess.run(["cuobjdump", "-lelf", capi.ENGINE_LIB], capture_output=True, text=True).stdout
