@@ -294,6 +294,16 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     for (unsigned v = tv; v < (unsigned)G::NV; v += TV) {
         const unsigned f0 = freq_of_pos<L>(v * R);
         float2 x0[R], x1[R];
+        // state rows of this virtual thread: issued before the butterfly so that their (L2) latency overlaps it
+        const unsigned rowStride = (L / R) * krs;
+        const unsigned off0 = kbase + f0 * krs;
+        float4 self[KIND == KS_SCALAR_Q2 ? R : 1];
+        if constexpr (KIND == KS_SCALAR_Q2) {
+            const float2* sp = ks.src[0] + off0;
+#pragma unroll
+            for (unsigned q = 0; q < R; ++q)
+                self[q] = valid ? __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         if (ks.hasFwd) {
 #pragma unroll
             for (unsigned q = 0; q < R; ++q) {
@@ -309,14 +319,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
         }
 
         if constexpr (KIND == KS_SCALAR_Q2) {
-            const unsigned rowStride = (L / R) * krs;
-            const unsigned off0 = kbase + f0 * krs;
-            const float2* sp = ks.src[0] + off0;
             float2* dp = ks.dst[0] + off0;
-            float4 self[R];
-#pragma unroll
-            for (unsigned q = 0; q < R; ++q)
-                self[q] = valid ? __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             const double tp[3] = {ks.sq2.tpre[0], ks.sq2.tpre[1], ks.sq2.tpre[2]};
             const double ip[4] = {ks.sq2.ipre[0], ks.sq2.ipre[1], ks.sq2.ipre[2], ks.sq2.ipre[3]};
             const bool termFused = ks.sq2.termFused != 0;
@@ -395,7 +398,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
 }
 
 template <int L, int KIND, int SIG>
-__global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB)
+__global__ void __launch_bounds__(AxisCfg<L>::THREADS, (AxisCfg<L>::MINB > 2 ? 2 : AxisCfg<L>::MINB))
 axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
     axis_kstage_body<L, KIND, SIG, void>(a, ks);
 }
