@@ -1128,7 +1128,11 @@ struct cupss_b200_plan {
         if (foldBarrier && nextPt == 1) return fail(CUPSS_B200_ERR_STATE, "internal: a single exchange point cannot order its own re-use");
         if (nextPt > XH_EPOCH / CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "too many exchange points (%d)", nextPt);
         for (cudaEvent_t& e : laneEv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        if (!laneEv.empty() && !side) CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        if (!laneEv.empty() && !side) {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));
+        }
         Launch b{};
         b.kind = Launch::BUMP;
         snprintf(b.name, sizeof b.name, "bump");
@@ -1247,7 +1251,12 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     p->useGraph = !(ng && ng[0] == '1');
     const char* np_ = getenv("CUPSS_B200_NO_PRUNE");
     p->prune = !(np_ && np_[0] == '1');
-    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    {   // main lane at the highest priority, the side lane (NVLink-bound pushed passes of a chunked exchange) at the lowest:
+        // a freed SM slot goes to the compute-bound kernel first
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));
     CK(cudaMalloc(&p->stepCounter, sizeof(unsigned int)));

@@ -162,6 +162,13 @@ template <int L> struct FftLevels;
             if (N_ > 3 && D_ < m) m = D_;                                                                             \
             return m;                                                                                                 \
         }                                                                                                             \
+        __host__ __device__ static constexpr int max_rad() {                                                          \
+            int m = A_;                                                                                               \
+            if (N_ > 1 && B_ > m) m = B_;                                                                             \
+            if (N_ > 2 && C_ > m) m = C_;                                                                             \
+            if (N_ > 3 && D_ > m) m = D_;                                                                             \
+            return m;                                                                                                 \
+        }                                                                                                             \
     };
 CUPSS_LEVELS(1, 1, 1, 1, 1, 1)
 CUPSS_LEVELS(2, 1, 2, 1, 1, 1)

@@ -31,7 +31,7 @@ constexpr int X_THREADS = 256;
 // SLOTS > 0: slots per CTA known at compile time (no stash: the line buffer is the whole slot); 0: run-time (XArgs).
 // SUMPOW (with FAST): several inputs, every monomial a power of one input -- accumulated on registers input by input.
 template <int SX, int MODE, bool FAST, int SLOTS, bool SUMPOW = false>
-__global__ void __launch_bounds__(X_THREADS, (FAST && !SUMPOW) ? 3 : 2) xpass_kernel(const __grid_constant__ XArgs a) {
+__global__ void __launch_bounds__(X_THREADS, (FAST && !SUMPOW && FftLevels<SX>::max_rad() <= 8) ? 3 : 2) xpass_kernel(const __grid_constant__ XArgs a) {
     using F = FftLevels<SX>;
     constexpr int n = F::n, LAST = n - 1, XB = XCfg<SX>::XB;
     using GL = LevelGeom<SX, LAST>;
