@@ -285,3 +285,49 @@ def test_multi_gpu_slab_partition_matches_single_gpu(built):
                         "--master-port", "29611", script], capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_GPU_OK" in r.stdout
+
+
+def _random_system(seed):
+    """A random but well-posed system in the reference's grammar: one or two dynamic fields with diffusive implicit parts,
+    a few constraint fields (gradients, a filtered copy, a product), random linear and product terms on the right."""
+    rng = np.random.default_rng(seed)
+    dim3 = bool(rng.integers(0, 2))
+    shape = (32, 16, 8) if dim3 else (64, 32, 1)
+    axes = ["iqx", "iqy"] + (["iqz"] if dim3 else [])
+    fields = [("u", 1), ("gu", 0), ("w", 0)]
+    eqs = []
+    a1, a2 = axes[rng.integers(0, len(axes))], axes[rng.integers(0, len(axes))]
+    two = bool(rng.integers(0, 2))
+    if two:
+        fields.append(("v", 1))
+    rhs_u = [f"- c1*{a1}*gu*u", f"+ c2*q^2*w", f"- c3*u^{int(rng.integers(2, 4))}"]
+    if two:
+        rhs_u.append(f"+ c4*{a2}*v*gu")
+    rng.shuffle(rhs_u)
+    eqs.append("dt u + (d1*q^2 + d2*q^4)*u = " + " ".join(rhs_u[: int(rng.integers(1, len(rhs_u) + 1))]).lstrip("+ "))
+    eqs.append(f"gu = {a1}*u")
+    eqs.append("w*(1 + q^2) = u^2" if rng.integers(0, 2) else f"w = {a2}*gu - 0.5*u")
+    if two:
+        eqs.append(f"dt v + d1*q^2*v = - c1*{a2}*u*v + c2*{a1}^2*w")
+    params = dict(c1=float(rng.uniform(0.2, 1.0)), c2=float(rng.uniform(0.2, 1.0)), c3=float(rng.uniform(0.2, 1.0)), c4=float(rng.uniform(0.2, 1.0)),
+                  d1=float(rng.uniform(0.5, 1.5)), d2=float(rng.uniform(0.1, 0.5)))
+    ic = dict(u=("smooth", (0.4, 0.04)))
+    if two:
+        ic["v"] = ("smooth", (0.3, 0.03))
+    return dict(shape=shape, dt=0.01, fields=fields, params=params, eqs=eqs, ic=ic, steps=25)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_systems_match_the_compiled_reference(built, seed):
+    """Fuzz over the plan machinery (several product groups, constraint fields with implicit parts, extra inverse
+    transforms, merged prefactors): product vs the reference CPU path (ORACLE-F) on the same random system."""
+    case = _random_system(seed)
+    got = cases.run_case(case)
+    want = cases.run_case(case, lib=ORACLE_F, device=0)
+    for f, _ in case["fields"]:
+        assert np.isfinite(want[f]).all(), (case["eqs"], f)
+        scale = np.linalg.norm(want[f])
+        if scale == 0:
+            assert np.linalg.norm(got[f]) == 0
+            continue
+        assert rel_l2(got[f], want[f]) < 2e-5, (case["eqs"], f, rel_l2(got[f], want[f]))
