@@ -331,3 +331,51 @@ def test_random_systems_match_the_compiled_reference(built, seed):
             assert np.linalg.norm(got[f]) == 0
             continue
         assert rel_l2(got[f], want[f]) < 2e-5, (case["eqs"], f, rel_l2(got[f], want[f]))
+
+
+def test_stochastic_run_matches_the_reference_statistically(built):
+    """North star: stochastic runs must match statistically.  Edwards-Wilkinson (examples/05) on 64^2: the time-averaged
+    structure factor S(q) = <|h_q|^2> of the product (Philox, generated in k-space) and of the reference CPU path
+    (mt19937 white noise in real space + FFT, seeded from the clock) agree bin by bin within the sampling error,
+    and both follow the discrete stationary spectrum nu^2 N / (c^2 - 1), c = 1 + dt D q^2."""
+    from cupss_b200.capi import Evolver
+    n, dt, D, dx = 64, 0.05, 1.0, 1.0
+    warm, samples, stride = 300, 120, 5
+
+    def spectrum(lib, device, seed=None):
+        ev = Evolver(device, n, n, 1, dx, dx, 1.0, dt, lib=lib)
+        ev.createField("h", True)
+        ev.addParameter("D", D)
+        ev.addEquation("dt h + D*q^2*h = 0")
+        ev.addNoise("h", "2*D")
+        if lib is None:
+            ev.setNoiseSeed(seed)
+        ev.prepareProblem()
+        ev.advanceTime(warm)
+        acc = np.zeros((n, n))
+        for _ in range(samples):
+            ev.advanceTime(stride)
+            if device:
+                ev.copyAllDataToHost()
+            acc += np.abs(np.fft.fft2(ev.real("h")[0].astype(np.float64))) ** 2
+        ev.close()
+        return acc / samples
+
+    sp = spectrum(None, 1, seed=2024)
+    sr = spectrum(ORACLE_F, 0)
+    q = 2 * np.pi * np.fft.fftfreq(n, d=dx)
+    q2 = q[None, :] ** 2 + q[:, None] ** 2
+    c = 1 + dt * D * q2
+    nu2 = 2 * D * dt / (dx * dx)
+    theory = np.where(q2 > 0, nu2 * n * n / np.maximum(c * c - 1, 1e-30), 0.0)
+    # radial bins with at least 40 modes each; only modes that have relaxed within the warm-up (c^(-2*warm) << 1)
+    relaxed = (q2 > 0) & (c ** (-2.0 * warm) < 1e-3)
+    edges = np.linspace(np.sqrt(q2[relaxed].min()), np.sqrt(q2.max()) * 1.0001, 9)
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        m = relaxed & (np.sqrt(q2) >= lo) & (np.sqrt(q2) < hi)
+        if m.sum() < 40:
+            continue
+        a, b, t = sp[m].mean(), sr[m].mean(), theory[m].mean()
+        # each mode's average over `samples` correlated snapshots has a relative error of a few x 1/sqrt(samples); a bin of >= 40 modes: ~3 %
+        assert abs(a / b - 1) < 0.12, ("product vs reference", lo, hi, a, b)
+        assert abs(a / t - 1) < 0.12 and abs(b / t - 1) < 0.12, ("vs stationary spectrum", lo, hi, a, b, t)
