@@ -274,9 +274,6 @@ struct Launch {
     double bytes = 0;   // algorithmic HBM bytes (A2A: bytes sent)
     double commBytes = 0;   // bytes this rank sends to other GPUs inside this launch (pushed exchange)
     XBarrier xb{};
-    // Two-lane schedule: lane 1 runs on a side stream (a parallel branch of the CUDA graph) so that the NVLink-bound
-    // pushed y pass of chunk c overlaps the x pass of chunk c+1.  waitEv / sigEv: event waited on before / recorded after.
-    int lane = 0, waitEv = -1, sigEv = -1;
     void* jitFn = nullptr;   // plan-specialised k stage compiled at run time (AXIS_KSTAGE), else the library's kernels
 };
 
@@ -302,15 +299,7 @@ struct cupss_b200_plan {
     std::map<int, float2*> twiddles;
     float* realBuf = nullptr;
     unsigned int* stepCounter = nullptr;
-    cudaStream_t stream = nullptr, side = nullptr;
-    std::vector<cudaEvent_t> laneEv;
-    // Measured on 2 x B200 (profiles/README.md): folding the flag exchange into the kernels costs a system-scope fence
-    // per CTA and is slower (1461 vs 1598 steps/s) than a 1-warp barrier kernel after the producer; z-chunk overlap of the
-    // x pass with the pushed y pass does not pay either (the NVLink-bound CTAs hold the SM's shared memory).  Both stay
-    // available for experiments: CUPSS_B200_FOLD_BARRIER=1, CUPSS_B200_XCHUNKS=n.
-    bool foldBarrier = false;
-    int xchunks = 1;
-    int pushPadKB = 0;         // CUPSS_B200_PUSH_PAD_KB: extra shared memory per CTA of a chunked pushed y pass (occupancy cap)
+    cudaStream_t stream = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     bool finalized = false;
     bool useGraph = true;
@@ -456,24 +445,10 @@ struct cupss_b200_plan {
         else { a.pushShift = ilog2(zl); a.pushMask = zl - 1; a.pushRs = (long long)kyl * pitch; a.pushBs = pitch; }               // z pass: batch = ky_local
         a.pushBase = (long long)kArenaHeader + (long long)slot * (long long)specElems + (long long)rank * zl * kyl * pitch;
         for (int d = 0; d < CUPSS_MAX_PEERS; ++d) a.push[d] = d < nranks ? peerArena[d] : nullptr;
-        a.rank = rank; a.nranks = nranks;
     }
-    // Producer / consumer roles of exchange point `pt` (folded barrier).  `total` = CTAs of all launches that push into it.
-    void set_signal(AxisArgs& a, int pt, unsigned total) { a.sigOn = foldBarrier ? 1 : 0; a.sigPt = pt; a.sigTotal = total; }
-    void set_wait(AxisArgs& a, int pt) {
-        a.waitOn = foldBarrier ? 1 : 0; a.waitPt = pt;
-        a.rank = rank; a.nranks = nranks;
-        for (int d = 0; d < CUPSS_MAX_PEERS; ++d) a.push[d] = d < nranks ? peerArena[d] : nullptr;
-    }
-    static unsigned axis_grid(const AxisArgs& a) { return (unsigned)a.ncolTiles * (unsigned)a.nbatch; }
-    int new_event() {
-        laneEv.push_back(nullptr);
-        return (int)laneEv.size() - 1;
-    }
-    // Returns the exchange point id.  With folded barriers no kernel is launched: the id is wired into the producer
-    // (set_signal) and the consumer (set_wait) instead.
-    int add_barrier(std::vector<Launch>& out, const char* nm) {
-        if (foldBarrier) return nextPt++;
+    // Cross-GPU barrier after a pushed exchange: a 1-warp kernel (kernels_axis.cu).  Measured alternatives that did not pay
+    // (profiles/README.md): flags folded into the producing / consuming kernels, z-chunked overlap with the x pass.
+    void add_barrier(std::vector<Launch>& out, const char* nm) {
         Launch l{};
         l.kind = Launch::XBAR;
         snprintf(l.name, sizeof l.name, "%s", nm);
@@ -482,17 +457,9 @@ struct cupss_b200_plan {
         l.xb.error = arena ? reinterpret_cast<int*>(arena) + 2048 : nullptr;
         l.xb.rank = rank; l.xb.nranks = nranks; l.xb.pt = nextPt++;
         out.push_back(l);
-        return l.xb.pt;
     }
 
-    int run_launch(Launch& l, bool lanes = true) {
-        cudaStream_t st = (lanes && l.lane == 1) ? side : stream;
-        if (lanes && l.waitEv >= 0) CK(cudaStreamWaitEvent(st, laneEv[l.waitEv], 0));
-        CKR(run_kernel(l, st));
-        if (lanes && l.sigEv >= 0) CK(cudaEventRecord(laneEv[l.sigEv], st));
-        return CUPSS_B200_OK;
-    }
-    int run_kernel(Launch& l, cudaStream_t stream) {
+    int run_launch(Launch& l) {
         switch (l.kind) {
             case Launch::XPASS: CK(launch_xpass(sx, l.mode, l.xa, stream)); break;
             case Launch::AXIS_PLAIN: CK(launch_axis_plain(l.L, l.dir, l.ax, stream)); break;
@@ -678,12 +645,6 @@ struct cupss_b200_plan {
         std::vector<const float2*> groupSpec(groups.size(), nullptr);   // input of the last-axis forward pass per group
 
         // ---- x passes (greedy split under the kernel's descriptor limits)
-        std::vector<Launch> xl;
-        int joinEv = -1;   // side-lane work the next main-lane launch has to wait for
-        auto push_main = [&](Launch& l) {
-            if (joinEv >= 0) { l.waitEv = joinEv; joinEv = -1; }
-            out.push_back(l);
-        };
         size_t g0 = 0;
         while (g0 < groups.size()) {
             Launch x{};
@@ -749,71 +710,12 @@ struct cupss_b200_plan {
             CKR(get_twiddle(sx, &x.xa.tw));
             CKR(get_twiddle_x3(&x.xa.tw3));
             x.bytes = (inFrac + x.xa.nOut) * spec_bytes();
-            xl.push_back(x);
+            out.push_back(x);
             g0 = g1;
         }
-        const bool pushFwd = dim == 3 && nranks > 1 && useP2P && !groups.empty();
-        if (!pushFwd) for (Launch& x : xl) out.push_back(x);
-        std::vector<int> ptOfGroup(groups.size(), -1);   // exchange point feeding each group's last-axis pass
 
         // ---- forward y passes (3-D) and slab exchange
-        if (pushFwd) {
-            // Fused exchange: the y pass stores each ky row straight into the owning peer's receive slot over NVLink.
-            // The slab is cut into z-chunks: the (NVLink-bound) pushed y pass of chunk c runs on the side lane while the
-            // (SM-bound) x pass of chunk c+1 runs on the main lane.
-            std::vector<Launch> yl;
-            for (size_t g = 0; g < groups.size(); ++g) {
-                Launch y{};
-                y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = -1;
-                snprintf(y.name, sizeof y.name, "yfwd_push_%s", tag);
-                CKR(make_y_axis(y.ax, true));
-                y.ax.in = groupSpec[g]; y.ax.out = nullptr;
-                y.bytes = 2.0 * spec_bytes();
-                const int slot = arenaNext++;
-                set_push(y.ax, slot, true);
-                y.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
-                ptOfGroup[g] = foldBarrier ? add_barrier(out, "xbar_fwd") : -1;   // folded: no launch, just the point id
-                if (foldBarrier) set_signal(y.ax, ptOfGroup[g], axis_grid(y.ax));
-                groupSpec[g] = arena_slot_ptr(rank, slot);
-                yl.push_back(y);
-            }
-            int nchunk = xchunks;
-            while (nchunk > 1 && (zl % nchunk || zl / nchunk < 4)) nchunk >>= 1;
-            const int cz = zl / nchunk;
-            for (int c = 0; c < nchunk; ++c) {
-                const long long lineOff = (long long)c * cz * sy * pitch;
-                int ev = -1;
-                for (size_t i = 0; i < xl.size(); ++i) {
-                    Launch x = xl[i];
-                    for (int q = 0; q < x.xa.nIn; ++q) x.xa.in[q] += lineOff;
-                    for (int q = 0; q < x.xa.nOut; ++q) x.xa.out[q] += lineOff;
-                    x.xa.nlines = (long long)cz * sy;
-                    x.bytes /= nchunk;
-                    if (nchunk > 1 && i + 1 == xl.size()) { ev = new_event(); x.sigEv = ev; }
-                    push_main(x);
-                }
-                for (size_t g = 0; g < yl.size(); ++g) {
-                    Launch y = yl[g];
-                    y.ax.in += lineOff;
-                    y.ax.pushBase += (long long)c * cz * y.ax.pushBs;
-                    y.ax.nbatch = cz;
-                    y.bytes /= nchunk; y.commBytes /= nchunk;
-                    if (nchunk > 1) {
-                        y.lane = 1;
-                        y.ax.extraSmem = pushPadKB * 1024;
-                        if (g == 0) y.waitEv = ev;
-                        if (c + 1 == nchunk && g + 1 == yl.size()) { joinEv = new_event(); y.sigEv = joinEv; }
-                    }
-                    out.push_back(y);
-                }
-            }
-            if (!foldBarrier)   // stand-alone barrier kernels: one per group, after all pushes (main lane, after the join)
-                for (size_t g = 0; g < groups.size(); ++g) {
-                    const size_t before = out.size();
-                    add_barrier(out, "xbar_fwd");
-                    if (joinEv >= 0 && out.size() > before) { out.back().waitEv = joinEv; joinEv = -1; }
-                }
-        } else if (dim == 3) {
+        if (dim == 3) {
             for (size_t g = 0; g < groups.size(); ++g) {
                 Launch y{};
                 y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = -1;
@@ -823,6 +725,17 @@ struct cupss_b200_plan {
                 CKR(get_scratch(sc++, &w4));
                 y.ax.in = groupSpec[g]; y.ax.out = w4;
                 y.bytes = 2.0 * spec_bytes();
+                if (nranks > 1 && useP2P) {
+                    // fused exchange: the y pass stores each ky row straight into the owning peer's receive slot over NVLink
+                    const int slot = arenaNext++;
+                    set_push(y.ax, slot, true);
+                    y.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+                    snprintf(y.name, sizeof y.name, "yfwd_push_%s", tag);
+                    out.push_back(y);
+                    add_barrier(out, "xbar_fwd");
+                    groupSpec[g] = arena_slot_ptr(rank, slot);
+                    continue;
+                }
                 out.push_back(y);
                 groupSpec[g] = w4;
                 if (nranks > 1) {
@@ -849,7 +762,6 @@ struct cupss_b200_plan {
         ks.seed = 0;
         ks.hasFwd = groups.empty() ? 0 : 1;
         if (ks.hasFwd) k.ax.in = groupSpec[0];
-        if (ks.hasFwd && ptOfGroup[0] >= 0) set_wait(k.ax, ptOfGroup[0]);
 
         std::map<int, int> srcOfField;
         auto srcField = [&](int f) -> int {
@@ -871,8 +783,7 @@ struct cupss_b200_plan {
             CKR(get_scratch(sc++, &that));
             z.ax.in = groupSpec[g]; z.ax.out = that;
             z.bytes = 2.0 * spec_bytes();
-            if (ptOfGroup[g] >= 0) set_wait(z.ax, ptOfGroup[g]);
-            push_main(z);
+            out.push_back(z);
             if (ks.nsrc >= KS_MAX_SRC) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
             ks.src[ks.nsrc] = that;
             srcOfGroup[g] = ks.nsrc++;
@@ -986,26 +897,18 @@ struct cupss_b200_plan {
         const bool pushInv = nranks > 1 && useP2P && dim == 3;
         std::vector<std::pair<int, float2*>> w1s;   // (field, input of its inverse y pass)
         std::vector<int> pushed;                    // same order: 1 if that input already sits in the local arena slot
-        std::vector<int> ptOfInv;                   // same order: exchange point the inverse y pass has to wait for (-1: none)
         if (ks.hasInv && pushInv) {
             const int slot = arenaNext++;
-            {   // set_push overwrites rank/nranks/push[] consistently with a set_wait done above
-                const int wOn = k.ax.waitOn, wPt = k.ax.waitPt;
-                set_push(k.ax, slot, false);
-                k.ax.waitOn = wOn; k.ax.waitPt = wPt;
-            }
+            set_push(k.ax, slot, false);
             k.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
             snprintf(k.name, sizeof k.name, "kstage_push_%s", tag);
-            const int pt = foldBarrier ? add_barrier(out, "xbar_inv") : -1;
-            if (foldBarrier) set_signal(k.ax, pt, axis_grid(k.ax));
-            push_main(k);
-            if (!foldBarrier) add_barrier(out, "xbar_inv");
+            out.push_back(k);
+            add_barrier(out, "xbar_inv");
             w1s.push_back({invField, arena_slot_ptr(rank, slot)});
             pushed.push_back(1);
-            ptOfInv.push_back(pt);
         } else {
-            push_main(k);
-            if (invField >= 0 && dim == 3) { w1s.push_back({invField, invOut}); pushed.push_back(0); ptOfInv.push_back(-1); }
+            out.push_back(k);
+            if (invField >= 0 && dim == 3) { w1s.push_back({invField, invOut}); pushed.push_back(0); }
         }
 
         // ---- remaining inverse transforms of dealiased fields
@@ -1032,17 +935,14 @@ struct cupss_b200_plan {
                 set_push(z.ax, slot, false);
                 z.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
                 snprintf(z.name, sizeof z.name, "lastinv_push_%s", tag);
-                const int pt = foldBarrier ? add_barrier(out, "xbar_inv") : -1;
-                if (foldBarrier) set_signal(z.ax, pt, axis_grid(z.ax));
                 out.push_back(z);
-                if (!foldBarrier) add_barrier(out, "xbar_inv");
+                add_barrier(out, "xbar_inv");
                 w1s.push_back({f, arena_slot_ptr(rank, slot)});
                 pushed.push_back(1);
-                ptOfInv.push_back(pt);
                 continue;
             }
             out.push_back(z);
-            if (dim == 3) { w1s.push_back({f, w1}); pushed.push_back(0); ptOfInv.push_back(-1); }
+            if (dim == 3) { w1s.push_back({f, w1}); pushed.push_back(0); }
         }
         for (size_t wi = 0; wi < w1s.size(); ++wi) {
             auto& pr = w1s[wi];
@@ -1059,7 +959,6 @@ struct cupss_b200_plan {
             CKR(make_y_axis(y.ax, false));
             y.ax.in = yin; y.ax.out = fields[pr.first].W2;
             y.bytes = 2.0 * spec_bytes();
-            if (ptOfInv[wi] >= 0) set_wait(y.ax, ptOfInv[wi]);
             if (prune) {
                 short cx, cy, cz;
                 cutoffs(fields[pr.first].aliasOrder, &cx, &cy, &cz);
@@ -1109,8 +1008,6 @@ struct cupss_b200_plan {
                 F.w2cut[0] = now[0]; F.w2cut[1] = now[1]; F.w2cut[2] = now[2];
             }
         }
-        for (cudaEvent_t e : laneEv) if (e) cudaEventDestroy(e);
-        laneEv.clear();
         if (nranks > 1 && useP2P) {
             // dry run to count the receive slots, then (collectively) size the arena and build for real
             std::vector<Launch> dry;
@@ -1120,19 +1017,11 @@ struct cupss_b200_plan {
             CKR(ensure_arena((size_t)arenaNext));
         }
         step.clear();
-        laneEv.clear();
         arenaNext = 0; nextPt = 0;
         CKR(build_stage(false, step));
         stageSplit = step.size();
         CKR(build_stage(true, step));
-        if (foldBarrier && nextPt == 1) return fail(CUPSS_B200_ERR_STATE, "internal: a single exchange point cannot order its own re-use");
         if (nextPt > XH_EPOCH / CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "too many exchange points (%d)", nextPt);
-        for (cudaEvent_t& e : laneEv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        if (!laneEv.empty() && !side) {
-            int lo = 0, hi = 0;
-            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));
-        }
         Launch b{};
         b.kind = Launch::BUMP;
         snprintf(b.name, sizeof b.name, "bump");
@@ -1251,12 +1140,7 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     p->useGraph = !(ng && ng[0] == '1');
     const char* np_ = getenv("CUPSS_B200_NO_PRUNE");
     p->prune = !(np_ && np_[0] == '1');
-    {   // main lane at the highest priority, the side lane (NVLink-bound pushed passes of a chunked exchange) at the lowest:
-        // a freed SM slot goes to the compute-bound kernel first
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, hi));
-    }
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));
     CK(cudaMalloc(&p->stepCounter, sizeof(unsigned int)));
@@ -1279,8 +1163,6 @@ void cupss_b200_destroy(cupss_b200_plan* p) {
         if (d != p->rank && p->peerArena[d]) cudaIpcCloseMemHandle(p->peerArena[d]);
     if (p->arena) cudaFree(p->arena);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
-    for (cudaEvent_t e : p->laneEv) if (e) cudaEventDestroy(e);
-    if (p->side) cudaStreamDestroy(p->side);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1307,12 +1189,6 @@ int cupss_b200_set_partition(cupss_b200_plan* p, int rank, int nranks, const voi
     if (nranks > CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "at most %d ranks", CUPSS_MAX_PEERS);
     const char* na = getenv("CUPSS_B200_NCCL_A2A");
     p->useP2P = !(na && na[0] == '1');
-    const char* xk = getenv("CUPSS_B200_FOLD_BARRIER");
-    p->foldBarrier = xk && xk[0] == '1';
-    const char* xc = getenv("CUPSS_B200_XCHUNKS");
-    if (xc && atoi(xc) >= 1) p->xchunks = atoi(xc);
-    const char* pp = getenv("CUPSS_B200_PUSH_PAD_KB");
-    if (pp && atoi(pp) >= 0) p->pushPadKB = atoi(pp);
     p->zl = p->sz / nranks; p->kyl = p->sy / nranks;
     p->specElems = (size_t)p->pitch * p->kyl * p->sz;   // == pitch * sy * zl
     return CUPSS_B200_OK;
@@ -1518,7 +1394,7 @@ int cupss_b200_profile_step(cupss_b200_plan* p, int nmax, char* names, float* ms
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaEventRecord(ev[0], p->stream));
     for (int i = 0; i < cnt; ++i) {
-        CKR(p->run_launch(p->step[i], false));
+        CKR(p->run_launch(p->step[i]));
         CK(cudaEventRecord(ev[i + 1], p->stream));
     }
     CK(cudaStreamSynchronize(p->stream));

@@ -40,19 +40,11 @@ struct AxisArgs {
     // buffer of peer (r >> pushShift) over NVLink:  push[peer] + pushBase + b*pushBs + (r & pushMask)*pushRs + col.
     int pushOn, pushShift, pushMask;
     long long pushRs, pushBs, pushBase;
-    float2* push[CUPSS_MAX_PEERS];   // base of every rank's exchange arena (header: flags / epochs / error / done counters)
-    // Exchange synchronisation folded into the kernels (no separate barrier launch):
-    //  producer (pushOn): the last CTA to finish (counted over all chunk launches of the exchange point, sigTotal CTAs)
-    //    bumps the local epoch of point sigPt and publishes it in every peer's flag table (st.release.sys);
-    //  consumer (waitOn): every CTA first waits until all peers have published the current epoch of point waitPt.
-    int sigOn, sigPt, rank, nranks;
-    unsigned int sigTotal;
-    int waitOn, waitPt;
-    int extraSmem;   // bytes of dynamic shared memory requested on top of the tile: caps the CTAs per SM of an NVLink-bound
-                     // pushed pass so that a pass on the other lane can share the SMs (0: off)
+    float2* push[CUPSS_MAX_PEERS];   // base of every rank's exchange arena (header: flags / epochs / error word)
+    int rank, nranks;
 };
-// Arena header layout (32-bit words from the arena base): flag table [pt][CUPSS_MAX_PEERS], epochs, error word, done counters.
-constexpr int XH_FLAGS = 0, XH_EPOCH = 1024, XH_ERROR = 2048, XH_DONE = 3072;
+// Arena header layout (32-bit words from the arena base): flag table [pt][CUPSS_MAX_PEERS], epochs, error word.
+constexpr int XH_FLAGS = 0, XH_EPOCH = 1024, XH_ERROR = 2048;
 
 // Cross-GPU barrier after a pushed exchange: every rank bumps its epoch for exchange point `pt`, publishes it in
 // flag[pt][rank] of every peer (release.sys) and waits until all peers have published theirs (acquire.sys).

@@ -65,18 +65,7 @@ static cudaError_t launch_plain_L(int dir, const AxisArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
     if (dir < 0) {
         if (a.maskOn) return cudaErrorInvalidValue;   // the mask only exists on inverse transforms
-        size_t smem = AxisCfg<L>::SMEM;
-        if (a.extraSmem > 0) {
-            static size_t grown = 0;
-            smem += (size_t)a.extraSmem;
-            if (smem > 220 * 1024) smem = 220 * 1024;
-            if (smem > grown) {
-                cudaError_t e = cudaFuncSetAttribute(axis_plain_kernel<L, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return e;
-                grown = smem;
-            }
-        }
-        axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, smem, st>>>(a);
+        axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
     } else if (a.maskOn) {
         axis_plain_kernel<L, 1, true><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
     } else {

@@ -38,46 +38,6 @@ __device__ __forceinline__ float2* axis_dst(const AxisArgs& a, float2* lbase, un
 __device__ __forceinline__ float4 ld4(const float2* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// ---------------------------------------------------------------- exchange synchronisation folded into the kernels
-// Consumer side: called by every CTA before it touches a receive slot.
-__device__ __forceinline__ void exchange_wait(const AxisArgs& a) {
-    if (!a.waitOn) return;
-    if (threadIdx.x == 0) {
-        unsigned int* hdr = reinterpret_cast<unsigned int*>(a.push[a.rank]);
-        const unsigned int target = *reinterpret_cast<volatile unsigned int*>(hdr + XH_EPOCH + a.waitPt);   // bumped by this GPU's own producer (stream order)
-        const long long t0 = clock64();
-        for (int d = 0; d < a.nranks; ++d) {
-            const unsigned int* f = hdr + XH_FLAGS + a.waitPt * CUPSS_MAX_PEERS + d;
-            unsigned int seen;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-                if (clock64() - t0 > 6000000000LL) { *reinterpret_cast<int*>(hdr + XH_ERROR) = 1; break; }   // ~3 s: a peer died; do not hang the GPU
-            } while ((int)(seen - target) < 0);
-        }
-    }
-    __syncthreads();
-}
-// Producer side: called by every CTA (also the ones that exit early) after its last store to a peer.
-__device__ __forceinline__ void exchange_signal(const AxisArgs& a) {
-    if (!a.sigOn) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int* hdr = reinterpret_cast<unsigned int*>(a.push[a.rank]);
-        __threadfence_system();                                   // this CTA's peer stores before the count
-        const unsigned int prev = atomicAdd(hdr + XH_DONE + a.sigPt, 1u);
-        if (prev + 1u == a.sigTotal) {                            // last CTA of the last chunk launch
-            __threadfence_system();                               // every other CTA's stores (fence-atomic-fence chain)
-            hdr[XH_DONE + a.sigPt] = 0u;
-            const unsigned int target = hdr[XH_EPOCH + a.sigPt] + 1u;
-            hdr[XH_EPOCH + a.sigPt] = target;
-            for (int d = 0; d < a.nranks; ++d) {
-                unsigned int* theirs = reinterpret_cast<unsigned int*>(a.push[d]) + XH_FLAGS + a.sigPt * CUPSS_MAX_PEERS + a.rank;
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(target) : "memory");
-            }
-        }
-    }
-}
-
 // 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed): the whole input tile of a CTA is put in flight by
 // its first few instructions, with no register staging, so the HBM latency is paid once per tile and overlaps the
 // arithmetic of the other CTAs resident on the SM.
@@ -144,9 +104,8 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     if (a.pruneOn) {   // CTA-uniform: the whole tile is outside the dealias cut-off -> output stays zero
         const int iyT = a.kyBase + (int)b;
         const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
-        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) { exchange_signal(a); return; }
+        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
     }
-    exchange_wait(a);
     auto load_twiddles = [&]() {
         for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
     };
@@ -211,7 +170,6 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
             tile_level<L, 0, DIR, TV>(tv, twS, sld, gst);
         }
     }
-    exchange_signal(a);
 }
 
 // PLAN: compile-time structure of the sweep for KIND == KS_JIT (kstage.cuh), void otherwise.
@@ -245,7 +203,6 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     float2* lbase = a.out + kbase;
     const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
 
-    exchange_wait(a);
     if constexpr (n > 1) {
         if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
     }
@@ -394,7 +351,6 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
             tile_level<L, 0, +1, TV>(tv, twS, sld, gst);
         }
     }
-    exchange_signal(a);
 }
 
 template <int L, int KIND, int SIG>
