@@ -64,12 +64,38 @@ def synthetic_ic(n, seed=1324):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons WHILE the timed region runs (B200_PROFILING.md clocks line).
+
+    NVML is polled from a thread of this process every few ms (the engine's C calls release the GIL), so even a
+    0.2 s timed region gets tens of samples; `nvidia-smi -lms` (whose start-up alone can outlast a short region) is
+    only the fallback when the NVML binding is missing."""
+
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nv, self.handle, self.thread, self.run = None, None, None, False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and all(v.strip().isdigit() for v in ids) and self.index < len(ids):
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+            self.nv, self.run = nv, True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -79,17 +105,36 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = ((nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for b, nm in bits:
+                    if r & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, polled every ~4 ms inside the timed region"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 7:
@@ -98,11 +143,11 @@ class ClockSampler:
                 sm.append(float(p[0])); mx.append(float(p[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[3:7]):
+            for nm, v in zip(self.NAMES, p[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_reference_rate(n_sample, steps, threads):
@@ -255,22 +300,30 @@ def main():
     e2e = None
     if not args.no_e2e:
         barrier()
+        # the host buffer of the public API is the float2 mirror `fieldsReal[name]` (value in .x): the user's IC is written
+        # there; the timed region starts with that (page-locked) host buffer filled and ends with the result back in it
         t0 = time.perf_counter()
         if ic is not None:
             ev.setReal(main_field(), ic)
+        t1 = time.perf_counter()
         ev.prepareProblem()
+        t2 = time.perf_counter()
         ev.advanceTime(args.steps)
+        ev.sync()
+        t3 = time.perf_counter()
         ev.copyAllDataToHost() if world == 1 else ev._lib.cupss_capi_copy_all_data_to_host(ev._h)
         _ = float(ev.fieldReal(main_field())[0, 0, 0, 0])
         barrier()
-        el = time.perf_counter() - t0
+        t4 = time.perf_counter()
+        el = t4 - t0
+        phases = {"fill_host_mirror_s": t1 - t0, "prepareProblem_h2d_s": t2 - t1, "steps_s": t3 - t2, "copyAllDataToHost_d2h_s": t4 - t3}
         if dist is not None:
             tt = torch.tensor([el], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             el = float(tt.item())
         slab_bytes = n * n * (n // world) * 8
         e2e = {"value": args.steps / el, "unit": "steps/s", "h2d_bytes_per_step": slab_bytes * world / args.steps,
-               "d2h_bytes_per_step": (2 if world == 1 else 1) * slab_bytes * world / args.steps, "seconds": el,
+               "d2h_bytes_per_step": (2 if world == 1 else 1) * slab_bytes * world / args.steps, "seconds": el, "phases": phases,
                "what": "setReal + prepareProblem (H2D) + K x advanceTime + copyAllDataToHost (D2H), wall clock"}
 
     launches = ev.launchesPerStep() * args.steps

@@ -54,6 +54,7 @@ _SIGS = {
     "cupss_capi_initialize_from_file": (None, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char]),
     "cupss_capi_dump_plan": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "cupss_capi_set_mirror_callback": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "cupss_capi_set_fourier_callback": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
 }
 
 # entry points that only the product build of the facade exports (tools/cupss_capi.h, CUPSS_B200_PRODUCT)
@@ -86,6 +87,8 @@ _ENGINE_SIGS = {
     "cupss_b200_step_stage": (C.c_int, [C.c_void_p, C.c_int]),
     "cupss_b200_real_view_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cupss_b200_real_view_commit": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "cupss_b200_comp_view_begin": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "cupss_b200_comp_view_commit": (C.c_int, [C.c_void_p, C.c_int]),
     "cupss_b200_field_alias": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cupss_b200_time_steps": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "cupss_b200_profile_step": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -309,6 +312,14 @@ class Evolver:
         """Install the facade's built-in host callback (mirror boundary condition) on a field of a RUN_CPU evolver."""
         if self._lib.cupss_capi_set_mirror_callback(self._h, name.encode(), 1 if odd else 0) != 0:
             raise KeyError(name)
+
+    def setFourierCallback(self, name: str, kind: int = 0, device_flavour: bool = False):
+        """Install one of the facade's built-in Fourier-space callbacks (field::callbackFourier; tools/cupss_capi.cpp)."""
+        rc = self._lib.cupss_capi_set_fourier_callback(self._h, name.encode(), int(kind), 1 if device_flavour else 0)
+        if rc == 1:
+            raise KeyError(name)
+        if rc != 0:
+            raise ValueError(f"Fourier callback kind {kind} (device_flavour={device_flavour}) is not available in this library")
 
     def dumpPlan(self) -> str:
         buf = C.create_string_buffer(1 << 16)

@@ -616,6 +616,64 @@ struct cupss_b200_plan {
         }
     }
 
+    // Masked inverse last-axis pass of field f (dealias mask + innermost inverse axis, src/field.cpp:199-232 + the first part
+    // of toReal); the caller sets out / push.
+    int lastinv_launch(int f, const char* tag, Launch& z) {
+        z = Launch{};
+        z.kind = Launch::AXIS_PLAIN; z.dir = +1;
+        snprintf(z.name, sizeof z.name, "lastinv_%s", tag);
+        CKR(make_last_axis(z.ax, &z.L));
+        z.ax.maskOn = 1;
+        short cx, cy, cz;
+        cutoffs(fields[f].aliasOrder, &cx, &cy, &cz);
+        z.ax.cutx = cx; z.ax.cuty = cy; z.ax.cutz = cz;
+        if (prune) {
+            z.ax.pruneOn = 1; z.ax.pruneCutX = cx; z.ax.pruneCutY = cy;
+            z.ax.rowCut = dim == 3 ? (cz < z.L ? cz : -1) : (cy < z.L ? cy : -1);
+        }
+        z.ax.in = fields[f].S;
+        z.bytes = 2.0 * spec_bytes();
+        return CUPSS_B200_OK;
+    }
+    // Inverse y pass (3-D) of the dealiased copy of field f into its W2, pruned to the dealias cut-off.
+    int yinv_launch(int f, const char* tag, const float2* yin, Launch& y) {
+        y = Launch{};
+        y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = +1;
+        snprintf(y.name, sizeof y.name, "yinv_%s", tag);
+        CKR(make_y_axis(y.ax, false));
+        y.ax.in = yin; y.ax.out = fields[f].W2;
+        y.bytes = 2.0 * spec_bytes();
+        if (prune) {
+            short cx, cy, cz;
+            cutoffs(fields[f].aliasOrder, &cx, &cy, &cz);
+            const int C = axis_tile_cols(sy);
+            y.ax.pruneOn = 1; y.ax.pruneCutX = cx; y.ax.pruneCutY = 32767;   // batch is z here: never pruned
+            y.ax.rowCut = cy < sy ? cy : -1;
+            const double fx = (double)std::min(ncol, (cx / C + 1) * C) / ncol;
+            y.bytes = fx * spec_bytes() * (1.0 + std::min(1.0, (2.0 * cy + 1.0) / sy));
+        }
+        return CUPSS_B200_OK;
+    }
+    // W2 of field f recomputed from its spectrum (after a Fourier-space callback changed S): field::dealias + toReal's
+    // strided-axis part, outside the fused k stage.  Single GPU.
+    int refresh_w2(int f) {
+        Field& F = fields[f];
+        if (!F.W2) return CUPSS_B200_OK;
+        std::vector<Launch> v;
+        Launch z;
+        CKR(lastinv_launch(f, "cb", z));
+        float2* w1 = F.W2;
+        if (dim == 3) CKR(get_scratch(0, &w1));
+        z.ax.out = w1;
+        v.push_back(z);
+        if (dim == 3) {
+            Launch y;
+            CKR(yinv_launch(f, "cb", w1, y));
+            v.push_back(y);
+        }
+        return run_list(v);
+    }
+
     int build_stage(bool dyn, std::vector<Launch>& out) {
         std::vector<int> outs;
         for (size_t f = 0; f < fields.size(); ++f) if (fields[f].dynamic == dyn) outs.push_back((int)f);
@@ -913,23 +971,11 @@ struct cupss_b200_plan {
 
         // ---- remaining inverse transforms of dealiased fields
         for (int f : extraInv) {
-            Launch z{};
-            z.kind = Launch::AXIS_PLAIN; z.dir = +1;
-            snprintf(z.name, sizeof z.name, "lastinv_%s", tag);
-            CKR(make_last_axis(z.ax, &z.L));
-            z.ax.maskOn = 1;
-            short cx, cy, cz;
-            cutoffs(fields[f].aliasOrder, &cx, &cy, &cz);
-            z.ax.cutx = cx; z.ax.cuty = cy; z.ax.cutz = cz;
-            if (prune) {
-                z.ax.pruneOn = 1; z.ax.pruneCutX = cx; z.ax.pruneCutY = cy;
-                z.ax.rowCut = dim == 3 ? (cz < z.L ? cz : -1) : (cy < z.L ? cy : -1);
-            }
-            z.ax.in = fields[f].S;
+            Launch z;
+            CKR(lastinv_launch(f, tag, z));
             float2* w1 = fields[f].W2;
             if (dim == 3) CKR(get_scratch(sc++, &w1));
             z.ax.out = w1;
-            z.bytes = 2.0 * spec_bytes();
             if (pushInv) {
                 const int slot = arenaNext++;
                 set_push(z.ax, slot, false);
@@ -953,21 +999,8 @@ struct cupss_b200_plan {
                 CKR(add_a2a(out, "a2a_inv", pr.second, r));
                 yin = r;
             }
-            Launch y{};
-            y.kind = Launch::AXIS_PLAIN; y.L = sy; y.dir = +1;
-            snprintf(y.name, sizeof y.name, "yinv_%s", tag);
-            CKR(make_y_axis(y.ax, false));
-            y.ax.in = yin; y.ax.out = fields[pr.first].W2;
-            y.bytes = 2.0 * spec_bytes();
-            if (prune) {
-                short cx, cy, cz;
-                cutoffs(fields[pr.first].aliasOrder, &cx, &cy, &cz);
-                const int C = axis_tile_cols(sy);
-                y.ax.pruneOn = 1; y.ax.pruneCutX = cx; y.ax.pruneCutY = 32767;   // batch is z here: never pruned
-                y.ax.rowCut = cy < sy ? cy : -1;
-                const double fx = (double)std::min(ncol, (cx / C + 1) * C) / ncol;
-                y.bytes = fx * spec_bytes() * (1.0 + std::min(1.0, (2.0 * cy + 1.0) / sy));
-            }
+            Launch y;
+            CKR(yinv_launch(pr.first, tag, yin, y));
             out.push_back(y);
         }
         return CUPSS_B200_OK;
@@ -1095,6 +1128,28 @@ struct cupss_b200_plan {
             CKR(run_launch(x));
         }
         return CUPSS_B200_OK;
+    }
+
+    // Fourier view of a field for callbackFourier (src/field.cpp:48-57): the full float2[sz][sy][sx] spectrum of the
+    // reference, rebuilt from the Hermitian half.  The commit keeps the Hermitian part of what the callback left --
+    // exactly what survives the reference's toReal -> normalize (real part) -> toComp that follows -- and redoes the
+    // dealiased copy, which the fused k stage had produced from the pre-callback spectrum.
+    int comp_view_begin(int f, float2** dev) {
+        if (nranks != 1) return fail(CUPSS_B200_ERR_ARG, "user callbacks are single-GPU only");
+        Field& F = fields[f];
+        if (!F.S) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
+        if (!viewBuf) CK(cudaMalloc(&viewBuf, (size_t)sx * sy * zl * sizeof(float2)));
+        CK(launch_spectrum_expand(F.S, viewBuf, sx, sy, sz, pitch, stream));
+        CK(cudaStreamSynchronize(stream));
+        *dev = viewBuf;
+        return CUPSS_B200_OK;
+    }
+    int comp_view_commit(int f) {
+        Field& F = fields[f];
+        if (!viewBuf) return fail(CUPSS_B200_ERR_STATE, "comp_view_commit without comp_view_begin");
+        CK(cudaDeviceSynchronize());   // the callback's kernels run on the legacy default stream
+        CK(launch_spectrum_compress(viewBuf, F.S, sx, sy, sz, pitch, stream));
+        return refresh_w2(f);
     }
 
     int do_steps(int n) {
@@ -1356,6 +1411,15 @@ int cupss_b200_real_view_begin(cupss_b200_plan* p, int f, int which, void** dev_
 int cupss_b200_real_view_commit(cupss_b200_plan* p, int f, int which) {
     CKR(check_field(p, f));
     return p->view_commit(f, which);
+}
+int cupss_b200_comp_view_begin(cupss_b200_plan* p, int f, void** dev_float2) {
+    CKR(check_field(p, f));
+    if (!dev_float2) return fail(CUPSS_B200_ERR_ARG, "null pointer");
+    return p->comp_view_begin(f, reinterpret_cast<float2**>(dev_float2));
+}
+int cupss_b200_comp_view_commit(cupss_b200_plan* p, int f) {
+    CKR(check_field(p, f));
+    return p->comp_view_commit(f);
 }
 int cupss_b200_sync(cupss_b200_plan* p) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");

@@ -75,6 +75,14 @@ CUPSS_HD float2 cfma_s(float2 u, float s, float2 c) {   // u*s + c, componentwis
 #endif
 }
 
+CUPSS_HD float2 cmul2(float2 a, float2 b) {   // componentwise product (FMUL2), NOT the complex product
+#ifdef __CUDA_ARCH__
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+
 // ---------------------------------------------------------------- constexpr trig (compile-time twiddles)
 constexpr double kPi = 3.14159265358979323846264338327950288;
 

@@ -94,6 +94,7 @@ cudaError_t launch_xpass(int sx, int mode, XArgs& a, cudaStream_t st);
 int xpass_max_inputs(int sx);   // inputs one launch can take (shared-memory stash)
 cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
 // float <-> float2 views of a real field (user callbacks see float2[N] with the value in .x, like the reference)
+cudaError_t launch_spectrum_compress(const float2* full, float2* half, int sx, int sy, int sz, int pitch, cudaStream_t st);
 cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStream_t st);
 cudaError_t launch_real_compress(const float2* in, float* out, size_t n, cudaStream_t st);
 // Hermitian half spectrum [sz][sy][pitch] -> full spectrum float2[sz][sy][sx] (comp_array layout of the reference)

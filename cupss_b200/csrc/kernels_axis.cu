@@ -187,6 +187,26 @@ cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int
     spectrum_expand_kernel<<<148 * 8, 256, 0, st>>>(half, full, sx, sy, sz, pitch);
     return cudaGetLastError();
 }
+// Hermitian part of a full spectrum, stored as the half spectrum: H(k) = (F(k) + conj F(-k)) / 2 for kx <= sx/2.
+// This is what the reference keeps of a user-modified comp_array: toReal -> normalize (real part) -> toComp
+// (src/field.cpp:59-66, 88-89).  Pad columns of the pitch stay untouched.
+__global__ void spectrum_compress_kernel(const float2* __restrict__ full, float2* __restrict__ half, int sx, int sy, int sz, int pitch) {
+    const int nc = sx / 2 + 1;
+    const size_t n = (size_t)nc * sy * sz;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(o % nc);
+        const size_t r = o / nc;
+        const int j = (int)(r % sy), k = (int)(r / sy);
+        const int mi = (sx - i) % sx, mj = (sy - j) % sy, mk = (sz - k) % sz;
+        const float2 a = full[((size_t)k * sy + j) * sx + i];
+        const float2 b = full[((size_t)mk * sy + mj) * sx + mi];
+        half[((size_t)k * sy + j) * pitch + i] = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    }
+}
+cudaError_t launch_spectrum_compress(const float2* full, float2* half, int sx, int sy, int sz, int pitch, cudaStream_t st) {
+    spectrum_compress_kernel<<<148 * 8, 256, 0, st>>>(full, half, sx, sy, sz, pitch);
+    return cudaGetLastError();
+}
 cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStream_t st) {
     real_expand_kernel<<<148 * 8, 256, 0, st>>>(in, out, n);
     return cudaGetLastError();

@@ -11,16 +11,19 @@
 //     and half the global load instructions;
 //   => 2 shared-memory round trips per point.
 // Replaces the same reference code as kernels_x.cu (/root/reference/src/field.cpp:247-298, src/term.cpp:48-102).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace cupss {
 
-template <int SX> struct X3Cfg {
+template <int SX, int NT> struct X3Cfg {
     static constexpr int R0 = SX == 512 ? 16 : (SX == 128 ? 8 : 0);
     static constexpr int R1 = 2 * R0;             // innermost radix = stride M of the strided level
     static constexpr int M = R1;
     static constexpr int TL = R0;                 // threads per job (complex line): M/2 mirror pairs == R0 innermost blocks
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = NT;            // 16 warps per SM either way (the kernel needs ~120 registers): NT = 256 -> 2 CTAs
+    static constexpr int CTAS = 512 / NT;         // of 8 warps, 128 -> 4 CTAs of 4 warps (finer barriers, more staggered phases)
     static constexpr int JOBS = THREADS / TL;
     static constexpr int LB = SX + 2 * R0;        // padded line, float2 elements: two pad elements after every R1
     static constexpr int TWLEN = (R0 - 1) * M;    // strided-level twiddles: entry (q-1)*M + j = exp(-2*pi*i*j*q/SX)
@@ -28,11 +31,11 @@ template <int SX> struct X3Cfg {
 };
 
 template <int SX>
-__device__ __forceinline__ unsigned x3pad(unsigned idx) { return idx + 2u * (idx / (unsigned)X3Cfg<SX>::R1); }
+__device__ __forceinline__ unsigned x3pad(unsigned idx) { return idx + 2u * (idx / (unsigned)X3Cfg<SX, 256>::R1); }
 
-template <int SX>
-__global__ void __launch_bounds__(X3Cfg<SX>::THREADS, 2) xpass3_kernel(const __grid_constant__ XArgs a) {
-    using Cfg = X3Cfg<SX>;
+template <int SX, int NT>
+__global__ void __launch_bounds__(NT, X3Cfg<SX, NT>::CTAS) xpass3_kernel(const __grid_constant__ XArgs a) {
+    using Cfg = X3Cfg<SX, NT>;
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1, M = Cfg::M, TL = Cfg::TL, LB = Cfg::LB, H = R0 / 2;
     extern __shared__ float2 smem2[];
     float2* twS = smem2;
@@ -91,7 +94,10 @@ __global__ void __launch_bounds__(X3Cfg<SX>::THREADS, 2) xpass3_kernel(const __g
         xb[x3pad<SX>(jA + M * q)] = xA[q];
         xb[x3pad<SX>(jB + M * q)] = xB[q];
     }
-    __syncthreads();
+    // a job's TL threads sit in ONE warp (TL divides 32) and its line is touched by nobody else: warp-level barriers are
+    // enough between the levels, so the warps of a CTA drift apart and their load / butterfly / store phases interleave
+    static_assert(32 % TL == 0, "a job must not straddle warps");
+    __syncwarp();
 
     // ------------------------------------------------ innermost level: inverse butterfly, product, forward butterfly
     {
@@ -103,28 +109,29 @@ __global__ void __launch_bounds__(X3Cfg<SX>::THREADS, 2) xpass3_kernel(const __g
             y[2 * i] = make_float2(v.x, v.y); y[2 * i + 1] = make_float2(v.z, v.w);
         }
         Dft<R1, +1>::run(y);
-        const float norm = a.norm;
-        const float c0 = a.mono[0].coef;
+        // both real lines of the job at once: (rx, ry) = y * norm, then the left-to-right product (r*r)*r of
+        // computeProduct (src/term.cpp:85-92) and the coefficient, as packed FMUL2 (same IEEE operations per component)
+        const float2 norm2 = make_float2(a.norm, a.norm);
+        const float2 c02 = make_float2(a.mono[0].coef, a.mono[0].coef);
         const bool cube = a.mono[0].nfac == 3;   // the launcher only sends single monomials c*r^2 / c*r^3 here (warp-uniform)
-        // r^3 is the left-to-right product (r*r)*r of computeProduct (src/term.cpp:85-92)
         if (cube) {
 #pragma unroll
             for (int i = 0; i < R1; ++i) {
-                const float rx = y[i].x * norm, ry = y[i].y * norm;
-                y[i] = make_float2(c0 * ((rx * rx) * rx), c0 * ((ry * ry) * ry));
+                const float2 r = cmul2(y[i], norm2);
+                y[i] = cmul2(c02, cmul2(cmul2(r, r), r));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < R1; ++i) {
-                const float rx = y[i].x * norm, ry = y[i].y * norm;
-                y[i] = make_float2(c0 * (rx * rx), c0 * (ry * ry));
+                const float2 r = cmul2(y[i], norm2);
+                y[i] = cmul2(c02, cmul2(r, r));
             }
         }
         Dft<R1, -1>::run(y);
 #pragma unroll
         for (int i = 0; i < R1 / 2; ++i) blk[i] = make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y);
     }
-    __syncthreads();
+    __syncwarp();
 
     // ------------------------------------------------ forward, strided level (twiddle, butterfly) + untangle on registers
 #pragma unroll
@@ -142,9 +149,12 @@ __global__ void __launch_bounds__(X3Cfg<SX>::THREADS, 2) xpass3_kernel(const __g
     // xA[r] = C[jA + M r], xB[r] = C[jB + M r];  A[k] = (C[k] + conj C[sx-k]) / 2,  B[k] = (C[k] - conj C[sx-k]) / (2i)
     float2* qa = a.out[0] + lA * a.pitch;
     float2* qb = a.out[0] + lB * a.pitch;
+    // 0.5*(u +- v) as fma(+-0.5, v, 0.5*u): the halvings are exact, so the single rounding is that of u +- v
+    const float2 half2 = make_float2(0.5f, 0.5f);
     auto emit = [&](unsigned k, float2 Ck, float2 Cm) {
-        if (hasA) qa[k] = make_float2(0.5f * (Ck.x + Cm.x), 0.5f * (Ck.y - Cm.y));
-        if (hasB) qb[k] = make_float2(0.5f * (Ck.y + Cm.y), -0.5f * (Ck.x - Cm.x));
+        const float2 h = cmul2(Ck, half2);
+        if (hasA) qa[k] = make_float2(fmaf(0.5f, Cm.x, h.x), fmaf(-0.5f, Cm.y, h.y));
+        if (hasB) qb[k] = make_float2(fmaf(0.5f, Cm.y, h.y), fmaf(0.5f, Cm.x, -h.x));
     };
 #pragma unroll
     for (int r = 0; r < H; ++r) {
@@ -156,28 +166,29 @@ __global__ void __launch_bounds__(X3Cfg<SX>::THREADS, 2) xpass3_kernel(const __g
     if (t0) emit(SX / 2, xA[H], xA[H]);
 }
 
-template <int SX>
+template <int SX, int NT>
 static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
-    using Cfg = X3Cfg<SX>;
+    using Cfg = X3Cfg<SX, NT>;
     static bool attr = false;
     if (!attr) {
         if (Cfg::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const long long njobs = (a.nlines + 1) / 2;
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
-    xpass3_kernel<SX><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    xpass3_kernel<SX, NT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
 bool xpass3_supported(int sx) { return sx == 512 || sx == 128; }
 
 cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st) {
-    if (sx == 512) return launch_x3_size<512>(a, st);
-    if (sx == 128) return launch_x3_size<128>(a, st);
+    static const int nt = [] { const char* e = getenv("CUPSS_B200_X3_THREADS"); return e ? atoi(e) : 128; }();   // measured (profiles/README.md): 0.202 ms at 128, 0.208 at 64, 0.229 at 256
+    if (sx == 512) return nt == 256 ? launch_x3_size<512, 256>(a, st) : (nt == 64 ? launch_x3_size<512, 64>(a, st) : launch_x3_size<512, 128>(a, st));
+    if (sx == 128) return launch_x3_size<128, 256>(a, st);
     return cudaErrorInvalidValue;
 }
 

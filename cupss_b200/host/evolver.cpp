@@ -246,11 +246,7 @@ void evolver::prepareProblem() {
     if (verbose) std::cout << "Building the fused per-equation plan." << std::endl;
     sendSystemToEngine();
     for (field *f : fields) {
-        if (f->hasCBFourier) {
-            std::cout << "ERROR: Fourier-space callbacks (field " << f->name << ") are not supported by the B200 engine" << std::endl;
-            std::exit(1);
-        }
-        if (f->hasCB && partRanks > 1) {
+        if ((f->hasCB || f->hasCBFourier) && partRanks > 1) {
             std::cout << "ERROR: user callbacks (field " << f->name << ") need a single-GPU run" << std::endl;
             std::exit(1);
         }
@@ -284,6 +280,26 @@ void evolver::applyCallback(field *f) {
     }
 }
 
+// field::setRHS' Fourier hook (src/field.cpp:48-57): the user function sees comp_array as the reference lays it out, the
+// full float2[sz][sy][sx] spectrum, right after the update and before dealias / toReal.
+void evolver::applyCallbackFourier(field *f) {
+    if (f->callbackFourier == NULL) {
+        std::cout << "Wants to apply callback function in Fourier space but pointer to function is NULL" << std::endl;
+        return;
+    }
+    const size_t n = (size_t)sx * sy * sz;
+    void *dev = nullptr;
+    engineCheck(cupss_b200_comp_view_begin(plan, f->engine_id, &dev), "comp_view_begin");
+    if (with_cuda) {
+        f->callbackFourier(this, static_cast<float2 *>(dev), sx, sy, sz);
+    } else {
+        if (cudaMemcpy(f->comp_array, dev, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) engineCheck(2, "callback download");
+        f->callbackFourier(this, f->comp_array, sx, sy, sz);
+        if (cudaMemcpy(dev, f->comp_array, n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) engineCheck(2, "callback upload");
+    }
+    engineCheck(cupss_b200_comp_view_commit(plan, f->engine_id), "comp_view_commit");
+}
+
 int evolver::advanceTime() {
     if (!plan) {
         std::cout << "ERROR: advanceTime called before prepareProblem" << std::endl;
@@ -292,15 +308,15 @@ int evolver::advanceTime() {
     if (currentTimeStep % writeEveryNSteps == 0) writeOut();
     if (planDirty) sendSystemToEngine();
     bool anyCB = false;
-    for (field *f : fields) anyCB = anyCB || f->hasCB;
+    for (field *f : fields) anyCB = anyCB || f->hasCB || f->hasCBFourier;
     if (!anyCB) {
         engineCheck(cupss_b200_step(plan, 1), "step");
     } else {
         // sweeps run eagerly with the callbacks in between, in the reference's order (constraint fields, then dynamic ones)
         engineCheck(cupss_b200_step_stage(plan, 0), "step_stage");
-        for (field *f : fields) if (!f->dynamic && f->hasCB) applyCallback(f);
+        for (field *f : fields) if (!f->dynamic) { if (f->hasCBFourier) applyCallbackFourier(f); if (f->hasCB) applyCallback(f); }
         engineCheck(cupss_b200_step_stage(plan, 1), "step_stage");
-        for (field *f : fields) if (f->dynamic && f->hasCB) applyCallback(f);
+        for (field *f : fields) if (f->dynamic) { if (f->hasCBFourier) applyCallbackFourier(f); if (f->hasCB) applyCallback(f); }
     }
     if (!with_cuda) {
         // reference-CPU semantics: host arrays are live after every step (examples/06_kpz reads them directly)

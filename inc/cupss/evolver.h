@@ -101,6 +101,7 @@ class evolver {
     bool seedFixed = false;
     int partRank = 0, partRanks = 1;
     char partId[128] = {0};
+    void applyCallbackFourier(field *f);   // field::setRHS' Fourier hook (src/field.cpp:48-57)
     void applyCallback(field *f);   // field::setRHS' callback hook (src/field.cpp:68-86)
     void sendSystemToEngine();   // implicit + terms + noise of every field -> C ABI, then finalize
     void engineCheck(int code, const char *what);

@@ -22,6 +22,8 @@
  *                                   plus every cufftExecC2C / curandGenerateNormal on that path)
  *   cupss_b200_step_stage +      field::setRHS callback hook: callback(system, real_array_d, ...) and, for a field that
  *   cupss_b200_real_view_*         products read, callback(system, real_dealiased_d, ...)             src/field.cpp:68-86
+ *   cupss_b200_comp_view_*       field::setRHS Fourier hook: callbackFourier(system, comp_array_d, ...) between the update
+ *                                and the dealias / toReal that follow it                              src/field.cpp:48-57
  *   cupss_b200_download_real     field::copyRealDeviceToHost (real_array)                    src/field.cpp:345-348
  *   cupss_b200_download_comp     field::copyDeviceToHost (comp_array)                        src/field.cpp:337-340
  *   cupss_b200_destroy           evolver/field/term dtors                                    src/evolver.cpp:40-45, src/field_init.cpp:156-189
@@ -88,6 +90,11 @@ int cupss_b200_step(cupss_b200_plan *p, int nsteps);   /* asynchronous on the pl
 int cupss_b200_step_stage(cupss_b200_plan *p, int stage);
 int cupss_b200_real_view_begin(cupss_b200_plan *p, int field, int which, void **dev_float2);
 int cupss_b200_real_view_commit(cupss_b200_plan *p, int field, int which);
+/* Fourier-space callbacks: after step_stage(s), for every flagged field of that sweep (before its real-space callback).
+ * The view is the reference's comp_array_d: the FULL float2[sz][sy][sx] spectrum.  commit keeps the Hermitian part of
+ * what the callback wrote (what the reference's toReal -> normalize -> toComp keeps) and recomputes the dealiased copy. */
+int cupss_b200_comp_view_begin(cupss_b200_plan *p, int field, void **dev_float2);
+int cupss_b200_comp_view_commit(cupss_b200_plan *p, int field);
 int cupss_b200_sync(cupss_b200_plan *p);
 
 /* Field flags computed by finalize (field::needsaliasing / aliasing_order, src/term_init.cpp:123-126). */

@@ -74,6 +74,23 @@ CASES = {
     #   examples/08_neumann_dirichlet_bc: odd BC (Dirichlet) on a diffusing field
     "bc_odd_diffusion_64": dict(shape=(64, 64, 1), dt=0.05, fields=[("phi", 1)], params={}, eqs=["dt phi + q^2*phi = 0"],
                                 ic=dict(phi=("droplet", (0.0, 1.0, 6.0, 2.0, 16, 16, 0))), steps=60, callbacks=[("phi", True)], device=0, oracle="U"),
+    # Fourier-space callbacks (field::callbackFourier, src/field.cpp:48-57), RUN_CPU flavour (host functions):
+    #   a Hermitian low-pass on the dynamic field of a Cahn-Hilliard run (the dealiased copy must follow the callback)
+    "fcb_lowpass_ch2d_64": dict(shape=(64, 64, 1), dt=0.1, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                                ic=dict(phi=("smooth", (0.1, 0.01))), steps=50, fourier_callbacks=[("phi", 1 - 1)], device=0, oracle="U"),
+    #   a callback that breaks the Hermitian symmetry: what survives is the real-part projection of field::normalize
+    "fcb_asym_ch3d_16": dict(shape=(16, 16, 16), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                             ic=dict(phi=("smooth", (0.5, 0.05))), steps=50, fourier_callbacks=[("phi", 1)], device=0, oracle="U"),
+    #   on a constraint field that a product reads, together with a real-space callback on the dynamic field
+    "fcb_constraint_kpz2d_32": dict(shape=(32, 32, 1), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0)], params=dict(l=0.5),
+                                    eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2", "iqxh = iqx*h", "iqyh = iqy*h"],
+                                    ic=dict(h=("smooth", (1.0, 0.1))), steps=40, fourier_callbacks=[("iqxh", 1), ("h", 0)],
+                                    callbacks=[("h", False)], device=0, oracle="U"),
+    #   a band of columns zeroed (1-D and 2-D; the same callback exists in a device flavour, see the test)
+    "fcb_band_diffusion_1d_64": dict(shape=(64, 1, 1), dt=0.05, fields=[("phi", 1)], params={}, eqs=["dt phi + q^2*phi = 0"],
+                                     ic=dict(phi=("smooth", (0.5, 0.2))), steps=20, fourier_callbacks=[("phi", 2)], device=0, oracle="U"),
+    "fcb_band_allen_cahn_2d_64": dict(shape=(64, 32, 1), dt=0.05, fields=[("phi", 1)], params={}, eqs=["dt phi + (q^2 - 1)*phi = -phi^3"],
+                                      ic=dict(phi=("smooth", (0.5, 0.2))), steps=40, fourier_callbacks=[("phi", 2)], device=0, oracle="U"),
     # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
     "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),
@@ -105,6 +122,8 @@ def build_system(case, lib=None, device=1):
         ev.addNoise(f, a)
     for f, odd in case.get("callbacks", []):
         ev.setMirrorCallback(f, odd)
+    for f, kind in case.get("fourier_callbacks", []):
+        ev.setFourierCallback(f, kind, device_flavour=bool(device) and lib is None and case.get("fourier_device_flavour", False))
     for name, (kind, args) in case["ic"].items():
         if kind == "smooth":
             ev.setReal(name, smooth_ic(sx, sy, sz, *args))

@@ -63,7 +63,8 @@ def test_reference_unit_tests_operators(built, dim, flavour):
 
 
 @pytest.mark.parametrize("name", ["diffusion2d_256", "ch2d_64", "ch2d_64_cpu_rule", "ch3d_32", "ch3d_64x32x16", "ch3d_128x16x16", "ch2d_512x16", "ch3d_512x8x8", "burgers_like_128",
-                                  "modelh_32", "kpz3d_32_det", "ops1d_16", "ops3d_16", "bc_even_inhomogeneous_64", "bc_odd_diffusion_64"])
+                                  "modelh_32", "kpz3d_32_det", "ops1d_16", "ops3d_16", "bc_even_inhomogeneous_64", "bc_odd_diffusion_64",
+                                  "fcb_lowpass_ch2d_64", "fcb_asym_ch3d_16", "fcb_constraint_kpz2d_32", "fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64"])
 def test_parity_with_compiled_reference(built, name):
     case = CASES[name]
     lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F
@@ -73,6 +74,24 @@ def test_parity_with_compiled_reference(built, name):
         scale = np.linalg.norm(want[f])
         assert scale > 0
         assert rel_l2(got[f], want[f]) < TOL, (f, rel_l2(got[f], want[f]))
+
+
+@pytest.mark.parametrize("name", ["fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64"])
+def test_fourier_callback_device_flavour_equals_host_flavour(built, name):
+    """RUN_GPU flavour: callbackFourier receives the DEVICE pointer of the full spectrum (comp_array_d, src/field.cpp:53-54);
+    the built-in device callback zeroes the same band with cudaMemset2D that the host callback zeroes in a loop."""
+    case = dict(CASES[name])
+    host = cases.run_case(case)                                   # RUN_CPU flavour of the product (host function)
+    case["device"], case["fourier_device_flavour"] = 1, True
+    dev = cases.run_case(case)                                    # RUN_GPU flavour (device pointer)
+    for f, _ in case["fields"]:
+        assert np.isfinite(dev[f]).all()
+        if case["shape"][1] == 1:
+            assert np.array_equal(dev[f], host[f]), (f, rel_l2(dev[f], host[f]))
+    if case["shape"][1] > 1:   # 2-D: the two flavours differ by the dealias rule (SURVEY.md 8c), so the witness is ORACLE-F + host callback
+        want = cases.run_case(dict(CASES[name]), lib=ORACLE_F, device=0)
+        for f, _ in case["fields"]:
+            assert rel_l2(dev[f], want[f]) < TOL, (f, rel_l2(dev[f], want[f]))
 
 
 @pytest.mark.parametrize("name", ["ch3d_32", "ch2d_64", "modelh_32"])

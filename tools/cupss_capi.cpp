@@ -144,6 +144,63 @@ int cupss_capi_set_mirror_callback(void *ev, const char *name, int odd)
     return 0;
 }
 
+/* Built-in FOURIER-space callbacks for tests (field::hasCBFourier / callbackFourier, installed like a user's main() would).
+ * They see comp_array as the reference lays it out: the full float2[sz][sy][sx] spectrum.
+ *   kind 0  smooth low-pass g(n) = 1 / (1 + 0.0005 |n|^2) on every mode (keeps the Hermitian symmetry)
+ *   kind 1  kind 0, then the modes 1 <= n_x <= 3 with n_y >= 0 are multiplied by 0.98 + 0.05 i on the POSITIVE-n_x side
+ *           only: the spectrum is no longer Hermitian, and what survives is decided by the real-part projection that
+ *           follows in field::setRHS
+ *   kind 2  the columns sx/8 <= i < sx/4 are zeroed (a contiguous band: the device flavour does it with cudaMemset2D) */
+static inline int signed_mode(int i, int n) { return i <= n / 2 ? i : i - n; }
+static void fourier_apply(float2 *a, int sx, int sy, int sz, int kind)
+{
+    for (int k = 0; k < sz; ++k)
+        for (int j = 0; j < sy; ++j)
+            for (int i = 0; i < sx; ++i) {
+                float2 &v = a[((size_t)k * sy + j) * sx + i];
+                const int ni = signed_mode(i, sx), nj = signed_mode(j, sy), nk = signed_mode(k, sz);
+                if (kind == 2) {
+                    if (i >= sx / 8 && i < sx / 4) { v.x = 0.0f; v.y = 0.0f; }
+                    continue;
+                }
+                const float g = 1.0f / (1.0f + 0.0005f * (float)(ni * ni + nj * nj + nk * nk));
+                v.x *= g; v.y *= g;
+                if (kind == 1 && ni >= 1 && ni <= 3 && nj >= 0) {
+                    const float re = 0.98f * v.x - 0.05f * v.y, im = 0.98f * v.y + 0.05f * v.x;
+                    v.x = re; v.y = im;
+                }
+            }
+}
+static void fourier_cb0(evolver *, float2 *a, int sx, int sy, int sz) { fourier_apply(a, sx, sy, sz, 0); }
+static void fourier_cb1(evolver *, float2 *a, int sx, int sy, int sz) { fourier_apply(a, sx, sy, sz, 1); }
+static void fourier_cb2(evolver *, float2 *a, int sx, int sy, int sz) { fourier_apply(a, sx, sy, sz, 2); }
+#ifdef CUPSS_B200_PRODUCT
+static void fourier_cb2_device(evolver *, float2 *a, int sx, int sy, int sz)   /* a is a DEVICE pointer (RUN_GPU flavour) */
+{
+    cudaMemset2D(a + sx / 8, (size_t)sx * sizeof(float2), 0, (size_t)(sx / 4 - sx / 8) * sizeof(float2), (size_t)sy * sz);
+}
+#endif
+
+int cupss_capi_set_fourier_callback(void *ev, const char *name, int kind, int device_flavour)
+{
+    if (EV(ev)->fieldsMap.find(name) == EV(ev)->fieldsMap.end()) return 1;
+    field *f = EV(ev)->fieldsMap[name];
+    if (device_flavour) {
+#ifdef CUPSS_B200_PRODUCT
+        if (kind != 2) return 2;
+        f->hasCBFourier = true;
+        f->callbackFourier = fourier_cb2_device;
+        return 0;
+#else
+        return 2;
+#endif
+    }
+    if (kind < 0 || kind > 2) return 2;
+    f->hasCBFourier = true;
+    f->callbackFourier = kind == 0 ? fourier_cb0 : (kind == 1 ? fourier_cb1 : fourier_cb2);
+    return 0;
+}
+
 int cupss_capi_dump_plan(void *ev, char *buf, int buflen)
 {
     evolver *e = EV(ev);

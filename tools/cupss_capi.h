@@ -45,6 +45,8 @@ void cupss_capi_initialize_half_system(void *ev, const char *name, float v1, flo
 void cupss_capi_initialize_from_file(void *ev, const char *name, const char *path, int skiprows, char delimiter);
 /* installs a built-in host callback (mirror boundary condition, even or odd) on a field: for RUN_CPU evolvers */
 int cupss_capi_set_mirror_callback(void *ev, const char *name, int odd);
+/* installs a built-in Fourier-space callback (kinds: see cupss_capi.cpp); device_flavour = 1 needs the product and RUN_GPU */
+int cupss_capi_set_fourier_callback(void *ev, const char *name, int kind, int device_flavour);
 /* textual dump of the parsed system from public members (fields, implicit pres, terms, products, noise, aliasing) */
 int cupss_capi_dump_plan(void *ev, char *buf, int buflen);
 
