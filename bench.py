@@ -300,11 +300,20 @@ def main():
     e2e = None
     if not args.no_e2e:
         barrier()
-        # the host buffer of the public API is the float2 mirror `fieldsReal[name]` (value in .x): the user's IC is written
-        # there; the timed region starts with that (page-locked) host buffer filled and ends with the result back in it
+        # The host buffer of the public API is the page-locked float2 mirror `fieldsReal[name]` (value in .x, the reference's
+        # layout); the user's initial condition is written there before the clock starts (it is user code, a numpy strided
+        # copy here).  Timed: prepareProblem (H2D upload + transform + plan), K x advanceTime, copyAllDataToHost (inverse
+        # transform + D2H of the real AND the Fourier array, as the reference does), result read on the host.
+        # One untimed pass of the same sequence first (3 steps): the first D2H of a process pays one-off driver set-up.
+        if ic is not None:
+            ev.setReal(main_field(), ic)
+        ev.prepareProblem()
+        ev.advanceTime(3)
+        ev.copyAllDataToHost() if world == 1 else ev._lib.cupss_capi_copy_all_data_to_host(ev._h)
         t0 = time.perf_counter()
         if ic is not None:
             ev.setReal(main_field(), ic)
+        barrier()
         t1 = time.perf_counter()
         ev.prepareProblem()
         t2 = time.perf_counter()
@@ -315,8 +324,8 @@ def main():
         _ = float(ev.fieldReal(main_field())[0, 0, 0, 0])
         barrier()
         t4 = time.perf_counter()
-        el = t4 - t0
-        phases = {"fill_host_mirror_s": t1 - t0, "prepareProblem_h2d_s": t2 - t1, "steps_s": t3 - t2, "copyAllDataToHost_d2h_s": t4 - t3}
+        el = t4 - t1
+        phases = {"untimed_fill_of_the_host_mirror_s": t1 - t0, "prepareProblem_h2d_s": t2 - t1, "steps_s": t3 - t2, "copyAllDataToHost_d2h_s": t4 - t3}
         if dist is not None:
             tt = torch.tensor([el], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -324,7 +333,7 @@ def main():
         slab_bytes = n * n * (n // world) * 8
         e2e = {"value": args.steps / el, "unit": "steps/s", "h2d_bytes_per_step": slab_bytes * world / args.steps,
                "d2h_bytes_per_step": (2 if world == 1 else 1) * slab_bytes * world / args.steps, "seconds": el, "phases": phases,
-               "what": "setReal + prepareProblem (H2D) + K x advanceTime + copyAllDataToHost (D2H), wall clock"}
+               "what": "host mirror filled -> prepareProblem (H2D) + K x advanceTime + copyAllDataToHost (D2H of real and Fourier arrays), wall clock, max over ranks"}
 
     launches = ev.launchesPerStep() * args.steps
     comm = ev.commBytesPerStep()

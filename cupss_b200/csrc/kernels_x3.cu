@@ -23,7 +23,7 @@ template <int SX, int NT> struct X3Cfg {
     static constexpr int M = R1;
     static constexpr int TL = R0;                 // threads per job (complex line): M/2 mirror pairs == R0 innermost blocks
     static constexpr int THREADS = NT;            // 16 warps per SM either way (the kernel needs ~120 registers): NT = 256 -> 2 CTAs
-    static constexpr int CTAS = 512 / NT;         // of 8 warps, 128 -> 4 CTAs of 4 warps (finer barriers, more staggered phases)
+    static constexpr int CTAS = 512 / NT;        // of 8 warps, 128 -> 4 CTAs of 4 warps (finer barriers, more staggered phases)
     static constexpr int JOBS = THREADS / TL;
     static constexpr int LB = SX + 2 * R0;        // padded line, float2 elements: two pad elements after every R1
     static constexpr int TWLEN = (R0 - 1) * M;    // strided-level twiddles: entry (q-1)*M + j = exp(-2*pi*i*j*q/SX)
@@ -33,8 +33,8 @@ template <int SX, int NT> struct X3Cfg {
 template <int SX>
 __device__ __forceinline__ unsigned x3pad(unsigned idx) { return idx + 2u * (idx / (unsigned)X3Cfg<SX, 256>::R1); }
 
-template <int SX, int NT>
-__global__ void __launch_bounds__(NT, X3Cfg<SX, NT>::CTAS) xpass3_kernel(const __grid_constant__ XArgs a) {
+template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS>
+__global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant__ XArgs a) {
     using Cfg = X3Cfg<SX, NT>;
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1, M = Cfg::M, TL = Cfg::TL, LB = Cfg::LB, H = R0 / 2;
     extern __shared__ float2 smem2[];
@@ -166,20 +166,20 @@ __global__ void __launch_bounds__(NT, X3Cfg<SX, NT>::CTAS) xpass3_kernel(const _
     if (t0) emit(SX / 2, xA[H], xA[H]);
 }
 
-template <int SX, int NT>
+template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS>
 static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
     using Cfg = X3Cfg<SX, NT>;
     static bool attr = false;
     if (!attr) {
         if (Cfg::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const long long njobs = (a.nlines + 1) / 2;
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
-    xpass3_kernel<SX, NT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    xpass3_kernel<SX, NT, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
