@@ -90,3 +90,28 @@ def test_committed_reference_runs_are_reproduced(built):
         out = cases.run_case(case, lib=ORACLE_U if case.get("oracle") == "U" else ORACLE_F, device=0)
         for f, arr in out.items():
             assert rel_l2(arr, gold[f"{name}/{f}"]) < 1e-6 or np.linalg.norm(gold[f"{name}/{f}"]) == 0
+
+
+def test_fourier_callback_semantics_of_the_reference(built):
+    """field::setRHS (src/field.cpp:48-66, 88-89) with a Fourier-space callback: the callback edits comp_array after the
+    update; toReal -> normalize keeps the REAL PART of the inverse transform; toComp transforms that back.  So what
+    survives of a callback that breaks the Hermitian symmetry is the Hermitian part of its output.  Restated in numpy
+    (float64) for one diffusion step with the facade's built-in callback of kind 1 and pinned on the compiled reference:
+    this is the rule the engine's comp_view_commit implements (cupss_b200/csrc/engine.cu)."""
+    sx, sy, dt = 32, 16, 0.05
+    case = dict(shape=(sx, sy, 1), dt=dt, fields=[("phi", 1)], params={}, eqs=["dt phi + q^2*phi = 0"],
+                ic=dict(phi=("smooth", (0.5, 0.2))), steps=1, fourier_callbacks=[("phi", 1)], device=0, oracle="U")
+    got = cases.run_case(case, lib=ORACLE_U, device=0)["phi"][0]
+    phi0 = cases.smooth_ic(sx, sy, 1, 0.5, 0.2)[0].astype(np.float64)
+    sm = lambda n: np.where(np.arange(n) <= n // 2, np.arange(n), np.arange(n) - n).astype(np.float64)   # the facade's signed_mode
+    ny, nx = np.meshgrid(sm(sy), sm(sx), indexing="ij")
+    q2 = (2 * np.pi * nx / sx) ** 2 + (2 * np.pi * ny / sy) ** 2
+    F = np.fft.fft2(phi0) / (1.0 + dt * q2)
+    F = F / (1.0 + 0.0005 * (nx ** 2 + ny ** 2))                       # kind 0 part: Hermitian low-pass
+    band = (nx >= 1) & (nx <= 3) & (ny >= 0)
+    F = np.where(band, F * (0.98 + 0.05j), F)                             # kind 1 part: one-sided, breaks the symmetry
+    want = np.fft.ifft2(F).real
+    assert rel_l2(got, want) < 5e-6, rel_l2(got, want)
+    # and it is NOT what a symmetry-preserving reading (apply the factor to both k and -k) would give
+    sym = np.fft.ifft2(np.where(band | ((nx <= -1) & (nx >= -3) & (ny <= 0)), F * 0 + np.fft.fft2(phi0) / (1.0 + dt * q2) / (1.0 + 0.0005 * (nx ** 2 + ny ** 2)) * 0.98, F)).real
+    assert rel_l2(got, sym) > 1e-3
