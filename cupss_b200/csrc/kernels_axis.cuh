@@ -238,6 +238,9 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     const float qyFix = wavenumber(iyFix, ks.sy, ks.stepqy);
     const float qxa2 = CUPSS_FMUL(qxa, qxa), qxb2 = CUPSS_FMUL(qxb, qxb);
     const float qyFix2 = CUPSS_FMUL(qyFix, qyFix);
+    // q^2 = (qx^2 + qy^2) + qz^2 in the reference's order; along y (2-D) the fixed part is qx^2 alone and the "+ 0" of the
+    // missing axis is the identity on a sum of squares
+    const float baseA = a.axis == 2 ? CUPSS_FADD(qxa2, qyFix2) : qxa2, baseB = a.axis == 2 ? CUPSS_FADD(qxb2, qyFix2) : qxb2;
     const bool fixY = (iyFix == 0) || (2 * iyFix == ks.sy);
     const bool fixSelfA = ((col == 0) || (2 * (int)col == ks.sx)) && fixY;
     const bool fixSelfB = (2 * ((int)col + 1) == ks.sx) && fixY;
@@ -259,7 +262,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
             const float2* sp = ks.src[0] + off0;
 #pragma unroll
             for (unsigned q = 0; q < R; ++q)
-                self[q] = valid ? __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                self[q] = __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride));   // columns up to the pitch exist: no predicate, stores are guarded
         }
         if (ks.hasFwd) {
 #pragma unroll
@@ -281,13 +284,20 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
             const double ip[4] = {ks.sq2.ipre[0], ks.sq2.ipre[1], ks.sq2.ipre[2], ks.sq2.ipre[3]};
             const bool termFused = ks.sq2.termFused != 0;
             const float dt = ks.dt;
+            // The pass runs along the whole last axis, so sRow == L and, with q unrolled, the sign of the mode number of
+            // row f0 + (L/R) q, its self-conjugacy and its distance from zero are known per q at compile time up to f0.
+            // (float)(f0 + c) == (float)f0 + (float)c exactly (integers below 2^24): one I2F per virtual thread.
+            const float f0f = (float)(int)f0;
+            const bool f00 = f0 == 0u;
 #pragma unroll
             for (unsigned q = 0; q < R; ++q) {
-                const int row = (int)(f0 + (L / R) * q);
-                const float qr = wavenumber(row, sRow, stepRow);
+                constexpr int STEP = L / R;
+                const bool neg = L > 1 && (int)q * STEP >= (L + 1) / 2;            // wavenumber(): i < (s+1)/2 ? i : i - s
+                const int row = (int)f0 + STEP * (int)q;
+                const float qr = CUPSS_FMUL(CUPSS_FADD(f0f, (float)(STEP * (int)q - (neg ? L : 0))), stepRow);
                 const float qr2 = CUPSS_FMUL(qr, qr);
-                const float q2a = CUPSS_FADD(CUPSS_FADD(qxa2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
-                const float q2b = CUPSS_FADD(CUPSS_FADD(qxb2, a.axis == 2 ? qyFix2 : qr2), a.axis == 2 ? qr2 : 0.0f);
+                const float q2a = CUPSS_FADD(baseA, qr2);
+                const float q2b = CUPSS_FADD(baseB, qr2);
                 float2 va, vb;
                 if constexpr (SIG >= 0) {
                     va = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
@@ -296,12 +306,13 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                     va = kstage_point_scalar_q2(ks.sq2, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
                     vb = kstage_point_scalar_q2(ks.sq2, dt, q2b, x1[q], make_float2(self[q].z, self[q].w));
                 }
-                const bool rowSelf = (row == 0) || (2 * row == sRow);
-                if (fixSelfA && rowSelf) va.y = 0.0f;
-                if (fixSelfB && rowSelf) vb.y = 0.0f;
+                if (q == 0 || 2 * q * STEP == (unsigned)L) {   // rows 0 and L/2 (f0 == 0 only) are self-conjugate
+                    if (fixSelfA && f00) va.y = 0.0f;
+                    if (fixSelfB && f00) vb.y = 0.0f;
+                }
                 if (!valid1) vb = make_float2(0.0f, 0.0f);   // padding column of the pitch
                 if (valid) st4(dp + q * rowStride, make_float4(va.x, va.y, vb.x, vb.y));
-                const int nr = row > sRow / 2 ? sRow - row : row;
+                const int nr = neg ? L - row : row;
                 const bool keepR = nr <= cutRow;
                 x0[q] = (keepA && keepR) ? va : make_float2(0.0f, 0.0f);
                 x1[q] = (keepB && keepR) ? vb : make_float2(0.0f, 0.0f);
