@@ -818,6 +818,9 @@ struct cupss_b200_plan {
         ks.sx = sx; ks.sy = sy; ks.sz = sz;
         ks.stepCounter = stepCounter;
         ks.seed = 0;
+        ks.noiseField = -1;
+        ks.whiteSelf = std::sqrt((float)sx * (float)sy * (float)sz);
+        ks.whitePair = std::sqrt(0.5f * ((float)sx * (float)sy * (float)sz));
         ks.hasFwd = groups.empty() ? 0 : 1;
         if (ks.hasFwd) k.ax.in = groupSpec[0];
 
@@ -892,7 +895,9 @@ struct cupss_b200_plan {
             od.noisy = F.noisy;
             if (F.noisy) {
                 od.noise.pre = F.noise.pre; od.noise.q2n = (signed char)F.noise.q2n; od.noise.invq = (signed char)F.noise.invq;
+                od.noiseAmp0 = std::sqrt(ks.noiseBase * F.noise.pre);
                 ks.seed = F.seed;
+                if (ks.noiseField < 0) ks.noiseField = f;
             }
             cutoffs(F.aliasOrder, &od.cutx, &od.cuty, &od.cutz);
             if (F.needsAlias) {

@@ -62,14 +62,20 @@ static cudaError_t launch_plain_L(int dir, const AxisArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
+    // pruned inverse passes: column tiles beyond the dealias cut-off produce nothing -- they are not launched at all
+    AxisArgs la = a;
+    if (a.pruneOn && dir > 0) {
+        const int live = a.pruneCutX / AxisCfg<L>::C + 1;
+        if (live < la.ncolTiles) la.ncolTiles = live;
+    }
+    const unsigned grid = (unsigned)la.ncolTiles * (unsigned)la.nbatch;
     if (dir < 0) {
         if (a.maskOn) return cudaErrorInvalidValue;   // the mask only exists on inverse transforms
-        axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+        axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);
     } else if (a.maskOn) {
-        axis_plain_kernel<L, 1, true><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+        axis_plain_kernel<L, 1, true><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);
     } else {
-        axis_plain_kernel<L, 1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a);
+        axis_plain_kernel<L, 1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);
     }
     return cudaGetLastError();
 }

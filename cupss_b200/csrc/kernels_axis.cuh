@@ -325,12 +325,19 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                 const int iz = a.axis == 2 ? row : 0;
                 const long long off = (long long)(kbase + (unsigned)row * krs);
                 float2 ra = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
+                KPoint ka = make_kpoint(ks, (int)col, iy, iz), kb = make_kpoint(ks, (int)col + 1, iy, iz);
+                if (ks.noiseField >= 0 && valid) {   // one generator call for both columns of the pair
+                    unsigned int c[4];
+                    philox_pair(ks, (int)(col >> 1), iy, iz, (unsigned int)ks.noiseField, step, c);
+                    ka.rnd0 = c[0]; ka.rnd1 = c[1]; kb.rnd0 = c[2]; kb.rnd1 = c[3];
+                    ka.rndField = kb.rndField = ks.noiseField;
+                }
                 if constexpr (KIND == KS_JIT) {
-                    if (valid) ra = kstage_point_plan<PLAN>(ks, make_kpoint(ks, (int)col, iy, iz), x0[0], off, step);
-                    if (valid1) rb = kstage_point_plan<PLAN>(ks, make_kpoint(ks, (int)col + 1, iy, iz), x1[0], off + 1, step);
+                    if (valid) ra = kstage_point_plan<PLAN>(ks, ka, x0[0], off, step);
+                    if (valid1) rb = kstage_point_plan<PLAN>(ks, kb, x1[0], off + 1, step);
                 } else {
-                    if (valid) ra = kstage_point(ks, make_kpoint(ks, (int)col, iy, iz), x0[0], off, step);
-                    if (valid1) rb = kstage_point(ks, make_kpoint(ks, (int)col + 1, iy, iz), x1[0], off + 1, step);
+                    if (valid) ra = kstage_point(ks, ka, x0[0], off, step);
+                    if (valid1) rb = kstage_point(ks, kb, x1[0], off + 1, step);
                 }
                 // rotate so that the loop body only ever touches register 0 and R-1 (rolled loop, static indices)
 #pragma unroll

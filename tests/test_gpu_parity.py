@@ -123,6 +123,30 @@ def test_parity_with_committed_reference_outputs(built):
             assert rel_l2(arr, gold[f"{name}/{f}"]) < TOL, (name, f)
 
 
+def test_cahn_hilliard_3d_full_size_matches_the_reference(built):
+    """BASELINE.json configs[2] at its FULL size (512^3) against the reference's own CPU path run in the build container
+    (tests/golden/make_golden_fullsize.py, ORACLE-F, 12 steps from the seeded smooth IC): 32^3 point samples, three full
+    planes and whole-field statistics, relative L2 <= 1e-5."""
+    path = os.path.join(cases.GOLDEN, "ch3d_512_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ch3d_512_ref.npz not generated")
+    sys.path.insert(0, cases.GOLDEN)
+    from make_golden_fullsize import summarise
+    gold = np.load(path)
+    case = dict(CASES["ch3d_32"])
+    case["shape"], case["steps"] = (512, 512, 512), int(gold["steps"][0])
+    got = summarise(cases.run_case(case)["phi"])
+    for k in ("sub", "plane_z", "plane_y", "plane_x"):
+        assert np.linalg.norm(gold[k]) > 0
+        assert rel_l2(got[k], gold[k]) < TOL, (k, rel_l2(got[k], gold[k]))
+    want = gold["stats"]
+    assert abs(got["stats"][0] - want[0]) < 2e-7 + 1e-5 * abs(want[0])            # mean (conserved)
+    for i in (1, 4):                                                                 # L2 norm, sum |phi|^3
+        assert abs(got["stats"][i] - want[i]) < 1e-5 * abs(want[i]), (i, got["stats"][i], want[i])
+    for i in (2, 3):                                                                 # extrema
+        assert abs(got["stats"][i] - want[i]) < 1e-4 * abs(want[i]), (i, got["stats"][i], want[i])
+
+
 def test_generic_and_lean_kstage_agree_bitwise(built):
     """KS_SCALAR_Q2 and the generic interpreter implement the same IEEE operation sequence."""
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
