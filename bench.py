@@ -72,8 +72,8 @@ class ClockSampler:
 
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_s=0.025):
+        self.index, self.proc, self.lines, self.period = index, None, [], period_s
         self.nv, self.handle, self.thread, self.run = None, None, None, False
         self.sm, self.mx, self.reasons = [], [], set()
 
@@ -118,7 +118,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -129,7 +129,7 @@ class ClockSampler:
             self.run = False
             self.thread.join(timeout=1.0)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, polled every ~4 ms inside the timed region"}
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": f"nvml, polled every {self.period * 1e3:.0f} ms inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--config", default="ch3d", choices=["ch3d", "kpz3d"], help="ch3d = the headline metric; kpz3d = BASELINE.json configs[4] (secondary)")
     ap.add_argument("--cpu-sample", type=int, default=128, help="grid edge of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--clock-period-ms", type=float, default=25.0, help="NVML clock / throttle-reason polling period inside the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -256,7 +257,7 @@ def main():
     ev.advanceTime(max(3, args.warmup))
     ev.sync()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_period_ms * 1e-3)
     if rank == 0:
         sampler.start()
     ms = ev.timeSteps(args.steps)
