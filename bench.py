@@ -190,7 +190,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "timesteps/s, Cahn-Hilliard 3D 512^3", "value": value, "unit": "steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"examples/03_cahn_hilliard_3d {n}^3, dt={DT}, deterministic", "l2": "n/a (CPU)"},
+            "config": {"workload": f"examples/03_cahn_hilliard_3d {n}^3, dt={DT}, a=-1 b=1 k=4, deterministic, IC 0.01*(2u-1)",
+                       "partition": "host cores of the box (reference CPU path, FFT shim threaded)", "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
