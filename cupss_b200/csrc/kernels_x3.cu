@@ -183,9 +183,10 @@ static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-bool xpass3_supported(int sx) { return sx == 512 || sx == 128; }
+bool xpass3_supported(int sx) { return sx == 512 || sx == 128 || xpass4_supported(sx); }
 
 cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st) {
+    if (xpass4_supported(sx)) return launch_xpass4(sx, a, st);   // long lines: the three-level kernel (kernels_x4.cu)
     static const int nt = [] { const char* e = getenv("CUPSS_B200_X3_THREADS"); return e ? atoi(e) : 128; }();   // measured (profiles/README.md): 0.202 ms at 128, 0.208 at 64, 0.229 at 256
     if (sx == 512) return nt == 256 ? launch_x3_size<512, 256>(a, st) : (nt == 64 ? launch_x3_size<512, 64>(a, st) : launch_x3_size<512, 128>(a, st));
     if (sx == 128) return launch_x3_size<128, 256>(a, st);
@@ -193,6 +194,7 @@ cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st) {
 }
 
 int host_x3_twiddles(int sx, float2* out) {
+    if (xpass4_supported(sx)) return host_x4_twiddles(sx, out);
     if (!xpass3_supported(sx)) return 0;
     const int R0 = sx == 512 ? 16 : 8, M = 2 * R0;
     for (int q = 1; q < R0; ++q)

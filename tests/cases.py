@@ -62,6 +62,17 @@ CASES = {
                         ic=dict(phi=("smooth", (0.4, 0.04))), steps=100),
     "ch3d_512x8x8": dict(shape=(512, 8, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
                          ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
+    # the three-level x kernel (kernels_x4.cu) covers sx = 1024, 2048, 4096 (configs[1] is 4096^2)
+    "ch2d_1024x32": dict(shape=(1024, 32, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                        ic=dict(phi=("smooth", (0.4, 0.04))), steps=100),
+    "ch2d_2048x32": dict(shape=(2048, 32, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                        ic=dict(phi=("smooth", (0.4, 0.04))), steps=100),
+    "ch2d_4096x32": dict(shape=(4096, 32, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
+                        ic=dict(phi=("smooth", (0.4, 0.04))), steps=100),
+    "ch3d_1024x32x8": dict(shape=(1024, 32, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                          ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
+    "burgers1d_2048": dict(shape=(2048, 1, 1), dt=0.01, fields=[("u", 1)], params=dict(nu=0.5), eqs=["dt u + nu*q^2*u = -0.5*iqx*u^2"],
+                           ic=dict(u=("smooth", (0.5, 0.05))), steps=100),
     # quadratic nonlinearity through the same kernel (single monomial c*r^2)
     "burgers_like_128": dict(shape=(128, 32, 1), dt=0.01, fields=[("u", 1)], params=dict(nu=0.5), eqs=["dt u + nu*q^2*u = -0.5*iqx*u^2"],
                              ic=dict(u=("smooth", (0.5, 0.05))), steps=100),
