@@ -27,6 +27,8 @@ def main():
     from cases import CASES, run_case, ORACLE_F, ORACLE_U
     out = {}
     for name, case in CASES.items():
+        if int(np.prod(case["shape"])) > 65536:
+            continue   # the long-line cases are checked against the oracle build directly; the fixture stays small
         lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F
         res = run_case(case, lib=lib, device=0)
         for field, arr in res.items():
