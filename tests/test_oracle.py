@@ -115,3 +115,23 @@ def test_fourier_callback_semantics_of_the_reference(built):
     # and it is NOT what a symmetry-preserving reading (apply the factor to both k and -k) would give
     sym = np.fft.ifft2(np.where(band | ((nx <= -1) & (nx >= -3) & (ny <= 0)), F * 0 + np.fft.fft2(phi0) / (1.0 + dt * q2) / (1.0 + 0.0005 * (nx ** 2 + ny ** 2)) * 0.98, F)).real
     assert rel_l2(got, sym) > 1e-3
+
+
+def test_smoke_checker_arm_is_a_real_run(built):
+    """The oracle arm of __graft_entry__.smoke() must hold the reference's RESULT: calling copyAllDataToHost on a RUN_CPU
+    reference evolver silently puts the initial condition back (its device arrays are never updated on that path)."""
+    import __graft_entry__ as ge
+    from cupss_b200.capi import RUN_CPU
+    n, ic = ge._smoke_case()
+    want = ge._smoke_run(ORACLE_F, RUN_CPU)
+    assert np.isfinite(want).all()
+    assert rel_l2(want, ic) > 0.05          # five steps moved the field
+    case = dict(CASES["ch3d_32"])
+    case["steps"] = 5
+    case["ic"] = {}
+    ev = cases.build_system(case, lib=ORACLE_F, device=0)
+    ev.setReal("phi", ic)
+    ev.prepareProblem()
+    ev.advanceTime(5)
+    assert np.array_equal(ev.real("phi"), want)
+    ev.close()
