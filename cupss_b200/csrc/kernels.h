@@ -109,6 +109,8 @@ int host_level_twiddles(int L, float2* out);
 bool xpass3_supported(int sx);
 int host_x3_twiddles(int sx, float2* out);
 cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st);
+bool xpass3_sumpow_supported(int sx);
+cudaError_t launch_xpass3_sumpow(int sx, XArgs& a, cudaStream_t st);
 // three-level variant for sx = 1024, 2048, 4096 (kernels_x4.cu); reached through the xpass3 entry points
 bool xpass4_supported(int sx);
 int host_x4_twiddles(int sx, float2* out);

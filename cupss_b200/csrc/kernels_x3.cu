@@ -166,6 +166,160 @@ __global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant_
     if (t0) emit(SX / 2, xA[H], xA[H]);
 }
 
+// Sum of powers (several inputs, one output, every monomial c * r_g^p with p <= 4 of ONE input -- the three squared
+// gradients of KPZ): the inverse levels run input by input and the monomials are accumulated on registers at the
+// innermost level, in monomial order like the generic kernels; one forward transform at the end.  128-thread CTAs,
+// three per SM (the accumulators need ~160 registers).
+template <int SX>
+__global__ void __launch_bounds__(128, 3) xpass3s_kernel(const __grid_constant__ XArgs a) {
+    using Cfg = X3Cfg<SX, 128>;
+    constexpr int R0 = Cfg::R0, R1 = Cfg::R1, M = Cfg::M, TL = Cfg::TL, LB = Cfg::LB, H = R0 / 2;
+    extern __shared__ float2 smem2[];
+    float2* twS = smem2;
+    const unsigned tid = threadIdx.x, job = tid / TL, t = tid % TL;
+    float2* xb = smem2 + Cfg::TWLEN + job * LB;
+
+    for (unsigned i = tid; i < (unsigned)Cfg::TWLEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw3 + i);
+
+    const long long jg = (long long)blockIdx.x * Cfg::JOBS + job;
+    const long long lA = 2 * jg, lB = lA + 1;
+    const bool hasA = lA < a.nlines, hasB = lB < a.nlines;
+    const bool t0 = t == 0;
+    const unsigned jA = t0 ? 0u : t, jB = t0 ? (unsigned)(M / 2) : (unsigned)M - t;   // the thread's two rows of the strided level
+    const float2 z = make_float2(0.0f, 0.0f);
+
+    float2 xA[R0], xB[R0];
+    // accumulator of the real-space term between inputs: a second line buffer per job, private to the thread that owns
+    // the innermost block (registers cannot hold it next to the strided level's 2 x R0 points without spilling)
+    float4* ab = reinterpret_cast<float4*>(smem2 + Cfg::TWLEN + Cfg::JOBS * LB + job * LB + t * (R1 + 2));
+    __syncthreads();   // twiddle table complete
+
+#pragma unroll 1
+    for (int g = 0; g < a.nIn; ++g) {
+    // ------------------------------------------------ inverse, strided level: form C from the half-spectrum lines
+    {
+        const float2* pa = a.in[g] + lA * a.pitch;
+        const float2* pb = a.in[g] + lB * a.pitch;
+        const int kmax = a.kmax[g];
+        float2 mA[H], mB[H];
+        auto form = [&](unsigned k, float2& c, float2& m) {   // c = A[k] + i B[k],  m = conj(A[k]) + i conj(B[k]) = C[sx - k]
+            const bool live = (int)k <= kmax;
+            float2 A = (live && hasA) ? __ldg(pa + k) : z;
+            float2 B = (live && hasB) ? __ldg(pb + k) : z;
+            if (k == 0 || 2 * k == SX) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of self-conjugate bins
+            c = make_float2(A.x - B.y, A.y + B.x);
+            m = make_float2(A.x + B.y, B.x - A.y);
+        };
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+            form(jA + M * q, xA[q], mA[q]);
+            form(jB + M * q, xB[q], mB[q]);
+        }
+        float2 cMid = z, mMid;
+        if (t0) form(SX / 2, cMid, mMid);   // k = sx/2 belongs to row 0 (register H of the thread that owns rows 0 and M/2)
+        // mirrors: rows (j, M - j) for t >= 1; row 0 mirrors onto itself and so does row M/2 for t == 0
+#pragma unroll
+        for (int i = 0; i < H; ++i) xB[H + i] = t0 ? mB[H - 1 - i] : mA[H - 1 - i];
+        xA[H] = t0 ? cMid : mB[H - 1];
+#pragma unroll
+        for (int i = 1; i < H; ++i) xA[H + i] = t0 ? mA[H - i] : mB[H - 1 - i];
+    }
+    Dft<R0, +1>::run(xA);
+    Dft<R0, +1>::run(xB);
+#pragma unroll
+    for (int q = 1; q < R0; ++q) {
+        xA[q] = cmul_conj(xA[q], twS[(q - 1) * M + jA]);
+        xB[q] = cmul_conj(xB[q], twS[(q - 1) * M + jB]);
+    }
+#pragma unroll
+    for (int q = 0; q < R0; ++q) {
+        xb[x3pad<SX>(jA + M * q)] = xA[q];
+        xb[x3pad<SX>(jB + M * q)] = xB[q];
+    }
+    // a job's TL threads sit in ONE warp (TL divides 32) and its line is touched by nobody else: warp-level barriers are
+    // enough between the levels, so the warps of a CTA drift apart and their load / butterfly / store phases interleave
+    static_assert(32 % TL == 0, "a job must not straddle warps");
+    __syncwarp();
+
+    // ------------------------------------------------ innermost level: inverse butterfly, this input's monomials
+    {
+        float2 y[R1];
+        const float4* blk = reinterpret_cast<const float4*>(xb + t * (R1 + 2));   // block t: R1 contiguous points (16-byte aligned)
+#pragma unroll
+        for (int i = 0; i < R1 / 2; ++i) {
+            const float4 v = blk[i];
+            y[2 * i] = make_float2(v.x, v.y); y[2 * i + 1] = make_float2(v.z, v.w);
+        }
+        Dft<R1, +1>::run(y);
+        const float2 norm2 = make_float2(a.norm, a.norm);
+#pragma unroll
+        for (int i = 0; i < R1; ++i) y[i] = cmul2(y[i], norm2);
+        // r^p is the left-to-right product ((r*r)*r)*r of computeProduct (src/term.cpp:85-92); both lines of the job at once.
+        // The launcher sends exactly one monomial per input, in input order (mono[g] belongs to input g).
+        const float2 cm = make_float2(a.mono[g].coef, a.mono[g].coef);
+        const int pm = a.mono[g].nfac;   // warp-uniform
+#pragma unroll
+        for (int i = 0; i < R1; ++i) {
+            float2 pw = y[i];
+            if (pm >= 2) pw = cmul2(pw, y[i]);
+            if (pm >= 3) pw = cmul2(pw, y[i]);
+            if (pm >= 4) pw = cmul2(pw, y[i]);
+            y[i] = cmul2(cm, pw);
+        }
+        if (g > 0) {   // add what the earlier inputs left, in input (= monomial) order
+#pragma unroll
+            for (int i = 0; i < R1 / 2; ++i) {
+                const float4 v = ab[i];
+                y[2 * i] = cadd(make_float2(v.x, v.y), y[2 * i]); y[2 * i + 1] = cadd(make_float2(v.z, v.w), y[2 * i + 1]);
+            }
+        }
+        if (g + 1 < a.nIn) {
+#pragma unroll
+            for (int i = 0; i < R1 / 2; ++i) ab[i] = make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y);
+        } else {
+            // last input: forward butterfly of the accumulated real-space term, straight from registers
+            Dft<R1, -1>::run(y);
+            float4* wb = reinterpret_cast<float4*>(xb + t * (R1 + 2));
+#pragma unroll
+            for (int i = 0; i < R1 / 2; ++i) wb[i] = make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y);
+        }
+    }
+    __syncwarp();   // the line buffer is re-used by the next input / read by the strided forward level
+    }   // inputs
+
+    // ------------------------------------------------ forward, strided level (twiddle, butterfly) + untangle on registers
+#pragma unroll
+    for (int q = 0; q < R0; ++q) {
+        xA[q] = xb[x3pad<SX>(jA + M * q)];
+        xB[q] = xb[x3pad<SX>(jB + M * q)];
+    }
+#pragma unroll
+    for (int q = 1; q < R0; ++q) {
+        xA[q] = cmul(xA[q], twS[(q - 1) * M + jA]);
+        xB[q] = cmul(xB[q], twS[(q - 1) * M + jB]);
+    }
+    Dft<R0, -1>::run(xA);
+    Dft<R0, -1>::run(xB);
+    // xA[r] = C[jA + M r], xB[r] = C[jB + M r];  A[k] = (C[k] + conj C[sx-k]) / 2,  B[k] = (C[k] - conj C[sx-k]) / (2i)
+    float2* qa = a.out[0] + lA * a.pitch;
+    float2* qb = a.out[0] + lB * a.pitch;
+    // 0.5*(u +- v) as fma(+-0.5, v, 0.5*u): the halvings are exact, so the single rounding is that of u +- v
+    const float2 half2 = make_float2(0.5f, 0.5f);
+    auto emit = [&](unsigned k, float2 Ck, float2 Cm) {
+        const float2 h = cmul2(Ck, half2);
+        if (hasA) qa[k] = make_float2(fmaf(0.5f, Cm.x, h.x), fmaf(-0.5f, Cm.y, h.y));
+        if (hasB) qb[k] = make_float2(fmaf(0.5f, Cm.y, h.y), fmaf(0.5f, Cm.x, -h.x));
+    };
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+        const float2 CmA = t0 ? xA[(R0 - r) % R0] : xB[R0 - 1 - r];
+        const float2 CmB = t0 ? xB[R0 - 1 - r] : xA[R0 - 1 - r];
+        emit(jA + M * r, xA[r], CmA);
+        emit(jB + M * r, xB[r], CmB);
+    }
+    if (t0) emit(SX / 2, xA[H], xA[H]);
+}
+
 template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS>
 static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
     using Cfg = X3Cfg<SX, NT>;
@@ -181,6 +335,35 @@ static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
     xpass3_kernel<SX, NT, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int SX>
+static cudaError_t launch_x3s_size(XArgs& a, cudaStream_t st) {
+    using Cfg = X3Cfg<SX, 128>;
+    constexpr size_t SMEM = Cfg::SMEM + (size_t)Cfg::JOBS * Cfg::LB * sizeof(float2);   // + the accumulator lines
+    static bool attr = false;
+    if (!attr) {
+        if (SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(xpass3s_kernel<SX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        attr = true;
+    }
+    const long long njobs = (a.nlines + 1) / 2;
+    const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
+    xpass3s_kernel<SX><<<grid, Cfg::THREADS, SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+// sum-of-powers variant: sx = 512 and 128 only (the three-level kernel has none yet)
+bool xpass3_sumpow_supported(int sx) {
+    static const bool off = [] { const char* e = getenv("CUPSS_B200_NO_X3S"); return e && e[0] == '1'; }();
+    return !off && (sx == 512 || sx == 128);
+}
+cudaError_t launch_xpass3_sumpow(int sx, XArgs& a, cudaStream_t st) {
+    if (sx == 512) return launch_x3s_size<512>(a, st);
+    if (sx == 128) return launch_x3s_size<128>(a, st);
+    return cudaErrorInvalidValue;
 }
 
 bool xpass3_supported(int sx) { return sx == 512 || sx == 128 || xpass4_supported(sx); }

@@ -109,6 +109,13 @@ CASES = {
     "kpz3d_32_det": dict(shape=(32, 32, 32), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0), ("iqzh", 0)], params=dict(l=0.5),
                          eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2 + l*iqzh^2", "iqxh = iqx*h", "iqyh = iqy*h", "iqzh = iqz*h"],
                          ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
+    # sum-of-powers x pass of the two-level kernel (sx = 128, 512): one power of each of several inputs, one output
+    "kpz3d_128x16x16_det": dict(shape=(128, 16, 16), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0), ("iqzh", 0)], params=dict(l=0.5),
+                                eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2 + l*iqzh^2", "iqxh = iqx*h", "iqyh = iqy*h", "iqzh = iqz*h"],
+                                ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
+    "kpz2d_512x16_mixed_powers": dict(shape=(512, 16, 1), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0)], params=dict(l=0.5, m=0.25),
+                                      eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + m*iqyh^3", "iqxh = iqx*h", "iqyh = iqy*h"],
+                                      ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
     # the reference's operator tests (tests/tests.cpp:191-422) extended to 3 steps
     "ops1d_16": dict(shape=(16, 1, 1), dt=0.1, fields=[("phi", 1), ("lapphi", 0), ("iqxphi", 0), ("invqphi", 0)], params={},
                      eqs=["dt phi + q^2*phi = iqxphi^2", "lapphi = -q^2*phi", "iqxphi = iqx*phi", "invqphi = 1/q*phi"],
