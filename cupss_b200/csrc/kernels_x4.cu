@@ -1,4 +1,5 @@
-// kernels_x4.cu -- three-level variant of the contiguous-axis pass for long lines, sx = 16 * R1 * 16 (1024, 2048, 4096), used
+// kernels_x4.cu -- three-level variant of the contiguous-axis pass for long lines, sx = 16 * R1 * 16 (1024, 2048, 4096; with a
+// trivial middle level also 256), used
 // like kernels_x3.cu when the real-space stage is one output of one input with a single monomial c*r^2 or c*r^3 (the
 // Cahn-Hilliard class; BASELINE.json configs[1] is 4096^2).
 //
@@ -30,7 +31,7 @@ template <int SX> struct X4Cfg {
     static constexpr int TW1 = (R1 - 1) * M1;     // level-1 twiddles: entry (q-1)*M1 + j = exp(-2*pi*i*j*q/N1)
     static constexpr size_t SMEM = ((size_t)TW1 + (size_t)JOBS * LB) * sizeof(float2);
     static_assert(M1 == R2, "the middle level's stride is the innermost block length");
-    static_assert(TJ == 32 || TJ == 64 || TJ == 128, "a job is 1, 2 or 4 warps");
+    static_assert(TJ == 8 || TJ == 32 || TJ == 64 || TJ == 128, "a job is part of one warp, or 1, 2 or 4 warps");
     static_assert(TW0 + TW1 <= SX, "the engine reserves sx table entries");
 };
 
@@ -39,7 +40,7 @@ __device__ __forceinline__ unsigned x4pad(unsigned idx) { return idx + 2u * (idx
 
 template <int TJ>
 __device__ __forceinline__ void job_sync(unsigned job) {
-    if constexpr (TJ == 32) __syncwarp();
+    if constexpr (TJ <= 32) __syncwarp();
     else if constexpr (TJ == 128) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(job + 1u), "n"(TJ) : "memory");
 }
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
     __syncthreads();   // level-1 twiddle table complete, level 0 of every job of the CTA stored
 
     // ------------------------------------------------ inverse, level 1 (shared -> shared)
+    if constexpr (R1 > 1) {
 #pragma unroll 1
     for (unsigned v = t; v < (unsigned)(SX / R1); v += TJ) {
         const unsigned blk = v / M1, j1 = v % M1, base = blk * N1 + j1;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
         for (int q = 0; q < R1; ++q) xb[x4pad<SX>(base + M1 * q)] = x[q];
     }
     job_sync<TJ>(job);
+    }
 
     // ------------------------------------------------ level 2: inverse butterfly, product, forward butterfly
     {
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
     job_sync<TJ>(job);
 
     // ------------------------------------------------ forward, level 1 (twiddle, butterfly; shared -> shared)
+    if constexpr (R1 > 1) {
 #pragma unroll 1
     for (unsigned v = t; v < (unsigned)(SX / R1); v += TJ) {
         const unsigned blk = v / M1, j1 = v % M1, base = blk * N1 + j1;
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
         for (int q = 0; q < R1; ++q) xb[x4pad<SX>(base + M1 * q)] = x[q];
     }
     job_sync<TJ>(job);
+    }
 
     // ------------------------------------------------ forward, level 0 (twiddle, butterfly) + untangle on registers
     {
@@ -229,10 +234,11 @@ static cudaError_t launch_x4_size(XArgs& a, cudaStream_t st) {
 
 bool xpass4_supported(int sx) {
     static const bool off = [] { const char* e = getenv("CUPSS_B200_NO_X4"); return e && e[0] == '1'; }();
-    return !off && (sx == 1024 || sx == 2048 || sx == 4096);
+    return !off && (sx == 256 || sx == 1024 || sx == 2048 || sx == 4096);
 }
 
 cudaError_t launch_xpass4(int sx, XArgs& a, cudaStream_t st) {
+    if (sx == 256) return launch_x4_size<256>(a, st);
     if (sx == 1024) return launch_x4_size<1024>(a, st);
     if (sx == 2048) return launch_x4_size<2048>(a, st);
     if (sx == 4096) return launch_x4_size<4096>(a, st);
@@ -240,7 +246,7 @@ cudaError_t launch_xpass4(int sx, XArgs& a, cudaStream_t st) {
 }
 
 int host_x4_twiddles(int sx, float2* out) {
-    if (sx != 1024 && sx != 2048 && sx != 4096) return 0;
+    if (sx != 256 && sx != 1024 && sx != 2048 && sx != 4096) return 0;
     const int R0 = 16, M0 = sx / R0, R1 = sx / 256, N1 = M0, M1 = N1 / R1;
     int n = 0;
     for (int q = 1; q < R0; ++q)

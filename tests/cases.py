@@ -63,6 +63,8 @@ CASES = {
     "ch3d_512x8x8": dict(shape=(512, 8, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
                          ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
     # the three-level x kernel (kernels_x4.cu) covers sx = 1024, 2048, 4096 (configs[1] is 4096^2)
+    "ch3d_256x16x8": dict(shape=(256, 16, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                          ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
     "ch2d_1024x32": dict(shape=(1024, 32, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
                         ic=dict(phi=("smooth", (0.4, 0.04))), steps=100),
     "ch2d_2048x32": dict(shape=(2048, 32, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
