@@ -115,6 +115,7 @@ cudaError_t launch_xpass3_sumpow(int sx, XArgs& a, cudaStream_t st);
 bool xpass4_supported(int sx);
 int host_x4_twiddles(int sx, float2* out);
 cudaError_t launch_xpass4(int sx, XArgs& a, cudaStream_t st);
+cudaError_t launch_xpass4_sumpow(int sx, XArgs& a, cudaStream_t st);
 bool fft_size_supported(int n);
 
 #endif

@@ -355,12 +355,13 @@ static cudaError_t launch_x3s_size(XArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// sum-of-powers variant: sx = 512 and 128 only (the three-level kernel has none yet)
+// sum-of-powers variants: the two-level kernel for sx = 512 and 128, the three-level one (kernels_x4.cu) for its sizes
 bool xpass3_sumpow_supported(int sx) {
     static const bool off = [] { const char* e = getenv("CUPSS_B200_NO_X3S"); return e && e[0] == '1'; }();
-    return !off && (sx == 512 || sx == 128);
+    return !off && (sx == 512 || sx == 128 || xpass4_supported(sx));
 }
 cudaError_t launch_xpass3_sumpow(int sx, XArgs& a, cudaStream_t st) {
+    if (xpass4_supported(sx)) return launch_xpass4_sumpow(sx, a, st);
     if (sx == 512) return launch_x3s_size<512>(a, st);
     if (sx == 128) return launch_x3s_size<128>(a, st);
     return cudaErrorInvalidValue;

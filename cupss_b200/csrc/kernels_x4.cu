@@ -215,6 +215,193 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
     }
 }
 
+// Sum of powers (several inputs, one output, ONE monomial c * r_g^p per input, mono[g] belonging to input g -- the three
+// squared gradients of KPZ): the inverse levels run input by input, the real-space term is accumulated in a second line
+// buffer private to the thread that owns the innermost block, one forward transform at the end.  Three CTAs per SM.
+template <int SX>
+__global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 3) xpass4s_kernel(const __grid_constant__ XArgs a) {
+    using Cfg = X4Cfg<SX>;
+    constexpr int R0 = Cfg::R0, R1 = Cfg::R1, R2 = Cfg::R2, M = Cfg::M0, N1 = Cfg::N1, M1 = Cfg::M1, TJ = Cfg::TJ, LB = Cfg::LB, H = R0 / 2;
+    extern __shared__ float2 smem2[];
+    float2* tw1S = smem2;
+    const unsigned tid = threadIdx.x, job = tid / TJ, t = tid % TJ;
+    float2* xb = smem2 + Cfg::TW1 + job * LB;
+    const float2* __restrict__ tw0 = a.tw3;
+
+    for (unsigned i = tid; i < (unsigned)Cfg::TW1; i += Cfg::THREADS) tw1S[i] = __ldg(a.tw3 + Cfg::TW0 + i);
+
+    const long long jg = (long long)blockIdx.x * Cfg::JOBS + job;
+    const long long lA = 2 * jg, lB = lA + 1;
+    const bool hasA = lA < a.nlines, hasB = lB < a.nlines;
+    const bool t0 = t == 0;
+    const unsigned jA = t0 ? 0u : t, jB = t0 ? (unsigned)(M / 2) : (unsigned)M - t;   // the thread's two rows of the strided level
+    const float2 z = make_float2(0.0f, 0.0f);
+    float2* ab = xb + Cfg::JOBS * LB;   // this job's accumulator line (same block layout as xb)
+    __syncthreads();   // level-1 twiddle table complete
+
+#pragma unroll 1
+    for (int g = 0; g < a.nIn; ++g) {
+    // ------------------------------------------------ inverse, level 0: form C from the half-spectrum lines
+    {
+        float2 xA[R0], xB[R0];
+        {
+            const float2* pa = a.in[g] + lA * a.pitch;
+            const float2* pb = a.in[g] + lB * a.pitch;
+            const int kmax = a.kmax[g];
+            float2 mA[H], mB[H];
+            auto form = [&](unsigned k, float2& c, float2& m) {   // c = A[k] + i B[k],  m = conj(A[k]) + i conj(B[k]) = C[sx - k]
+                const bool live = (int)k <= kmax;
+                float2 A = (live && hasA) ? __ldg(pa + k) : z;
+                float2 B = (live && hasB) ? __ldg(pb + k) : z;
+                if (k == 0 || 2 * k == SX) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of self-conjugate bins
+                c = make_float2(A.x - B.y, A.y + B.x);
+                m = make_float2(A.x + B.y, B.x - A.y);
+            };
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                form(jA + M * q, xA[q], mA[q]);
+                form(jB + M * q, xB[q], mB[q]);
+            }
+            float2 cMid = z, mMid;
+            if (t0) form(SX / 2, cMid, mMid);   // k = sx/2 belongs to row 0 (register H of the thread that owns rows 0 and M/2)
+#pragma unroll
+            for (int i = 0; i < H; ++i) xB[H + i] = t0 ? mB[H - 1 - i] : mA[H - 1 - i];
+            xA[H] = t0 ? cMid : mB[H - 1];
+#pragma unroll
+            for (int i = 1; i < H; ++i) xA[H + i] = t0 ? mA[H - i] : mB[H - 1 - i];
+        }
+        Dft<R0, +1>::run(xA);
+        Dft<R0, +1>::run(xB);
+#pragma unroll
+        for (int q = 1; q < R0; ++q) {
+            xA[q] = cmul_conj(xA[q], __ldg(tw0 + (q - 1) * M + jA));
+            xB[q] = cmul_conj(xB[q], __ldg(tw0 + (q - 1) * M + jB));
+        }
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+            xb[x4pad<SX>(jA + M * q)] = xA[q];
+            xb[x4pad<SX>(jB + M * q)] = xB[q];
+        }
+    }
+    job_sync<TJ>(job);
+
+    // ------------------------------------------------ inverse, level 1 (shared -> shared)
+    if constexpr (R1 > 1) {
+#pragma unroll 1
+    for (unsigned v = t; v < (unsigned)(SX / R1); v += TJ) {
+        const unsigned blk = v / M1, j1 = v % M1, base = blk * N1 + j1;
+        float2 x[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) x[q] = xb[x4pad<SX>(base + M1 * q)];
+        Dft<R1, +1>::run(x);
+#pragma unroll
+        for (int q = 1; q < R1; ++q) x[q] = cmul_conj(x[q], tw1S[(q - 1) * M1 + j1]);
+#pragma unroll
+        for (int q = 0; q < R1; ++q) xb[x4pad<SX>(base + M1 * q)] = x[q];
+    }
+    job_sync<TJ>(job);
+    }
+
+    // ------------------------------------------------ level 2: inverse butterfly, this input's monomial, accumulate
+    {
+        // both real lines of the job at once; r^p is the left-to-right product ((r*r)*r)*r of computeProduct (src/term.cpp:85-92)
+        const float2 norm2 = make_float2(a.norm, a.norm);
+        const float2 cm = make_float2(a.mono[g].coef, a.mono[g].coef);
+        const int pm = a.mono[g].nfac;   // warp-uniform
+        const bool last = g + 1 == a.nIn;
+#pragma unroll 1
+        for (unsigned b = t; b < (unsigned)(SX / R2); b += TJ) {
+            float2 y[R2];
+            float4* blk = reinterpret_cast<float4*>(xb + b * (R2 + 2));   // block b: R2 contiguous points (16-byte aligned)
+            float4* abk = reinterpret_cast<float4*>(ab + b * (R2 + 2));
+#pragma unroll
+            for (int i = 0; i < R2 / 2; ++i) {
+                const float4 v = blk[i];
+                y[2 * i] = make_float2(v.x, v.y); y[2 * i + 1] = make_float2(v.z, v.w);
+            }
+            Dft<R2, +1>::run(y);
+#pragma unroll
+            for (int i = 0; i < R2; ++i) {
+                const float2 r = cmul2(y[i], norm2);
+                float2 pw = r;
+                if (pm >= 2) pw = cmul2(pw, r);
+                if (pm >= 3) pw = cmul2(pw, r);
+                if (pm >= 4) pw = cmul2(pw, r);
+                y[i] = cmul2(cm, pw);
+            }
+            if (g > 0) {   // add what the earlier inputs left, in input (= monomial) order
+#pragma unroll
+                for (int i = 0; i < R2 / 2; ++i) {
+                    const float4 v = abk[i];
+                    y[2 * i] = cadd(make_float2(v.x, v.y), y[2 * i]); y[2 * i + 1] = cadd(make_float2(v.z, v.w), y[2 * i + 1]);
+                }
+            }
+            if (!last) {
+#pragma unroll
+                for (int i = 0; i < R2 / 2; ++i) abk[i] = make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y);
+            } else {
+                Dft<R2, -1>::run(y);
+#pragma unroll
+                for (int i = 0; i < R2 / 2; ++i) blk[i] = make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y);
+            }
+        }
+    }
+    job_sync<TJ>(job);   // the line buffer is re-used by the next input / read by the forward levels
+    }   // inputs
+
+    // ------------------------------------------------ forward, level 1 (twiddle, butterfly; shared -> shared)
+    if constexpr (R1 > 1) {
+#pragma unroll 1
+    for (unsigned v = t; v < (unsigned)(SX / R1); v += TJ) {
+        const unsigned blk = v / M1, j1 = v % M1, base = blk * N1 + j1;
+        float2 x[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) x[q] = xb[x4pad<SX>(base + M1 * q)];
+#pragma unroll
+        for (int q = 1; q < R1; ++q) x[q] = cmul(x[q], tw1S[(q - 1) * M1 + j1]);
+        Dft<R1, -1>::run(x);
+#pragma unroll
+        for (int q = 0; q < R1; ++q) xb[x4pad<SX>(base + M1 * q)] = x[q];
+    }
+    job_sync<TJ>(job);
+    }
+
+    // ------------------------------------------------ forward, level 0 (twiddle, butterfly) + untangle on registers
+    {
+        float2 xA[R0], xB[R0];
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+            xA[q] = xb[x4pad<SX>(jA + M * q)];
+            xB[q] = xb[x4pad<SX>(jB + M * q)];
+        }
+#pragma unroll
+        for (int q = 1; q < R0; ++q) {
+            xA[q] = cmul(xA[q], __ldg(tw0 + (q - 1) * M + jA));
+            xB[q] = cmul(xB[q], __ldg(tw0 + (q - 1) * M + jB));
+        }
+        Dft<R0, -1>::run(xA);
+        Dft<R0, -1>::run(xB);
+        // xA[r] = C[jA + M r], xB[r] = C[jB + M r];  A[k] = (C[k] + conj C[sx-k]) / 2,  B[k] = (C[k] - conj C[sx-k]) / (2i)
+        float2* qa = a.out[0] + lA * a.pitch;
+        float2* qb = a.out[0] + lB * a.pitch;
+        // 0.5*(u +- v) as fma(+-0.5, v, 0.5*u): the halvings are exact, so the single rounding is that of u +- v
+        const float2 half2 = make_float2(0.5f, 0.5f);
+        auto emit = [&](unsigned k, float2 Ck, float2 Cm) {
+            const float2 h = cmul2(Ck, half2);
+            if (hasA) qa[k] = make_float2(fmaf(0.5f, Cm.x, h.x), fmaf(-0.5f, Cm.y, h.y));
+            if (hasB) qb[k] = make_float2(fmaf(0.5f, Cm.y, h.y), fmaf(0.5f, Cm.x, -h.x));
+        };
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const float2 CmA = t0 ? xA[(R0 - r) % R0] : xB[R0 - 1 - r];
+            const float2 CmB = t0 ? xB[R0 - 1 - r] : xA[R0 - 1 - r];
+            emit(jA + M * r, xA[r], CmA);
+            emit(jB + M * r, xB[r], CmB);
+        }
+        if (t0) emit(SX / 2, xA[H], xA[H]);
+    }
+}
+
 template <int SX>
 static cudaError_t launch_x4_size(XArgs& a, cudaStream_t st) {
     using Cfg = X4Cfg<SX>;
@@ -230,6 +417,32 @@ static cudaError_t launch_x4_size(XArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
     xpass4_kernel<SX><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int SX>
+static cudaError_t launch_x4s_size(XArgs& a, cudaStream_t st) {
+    using Cfg = X4Cfg<SX>;
+    constexpr size_t SMEM = Cfg::SMEM + (size_t)Cfg::JOBS * Cfg::LB * sizeof(float2);   // + the accumulator lines
+    static bool attr = false;
+    if (!attr) {
+        if (SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(xpass4s_kernel<SX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        attr = true;
+    }
+    const long long njobs = (a.nlines + 1) / 2;
+    const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
+    xpass4s_kernel<SX><<<grid, Cfg::THREADS, SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xpass4_sumpow(int sx, XArgs& a, cudaStream_t st) {
+    if (sx == 256) return launch_x4s_size<256>(a, st);
+    if (sx == 1024) return launch_x4s_size<1024>(a, st);
+    if (sx == 2048) return launch_x4s_size<2048>(a, st);
+    if (sx == 4096) return launch_x4s_size<4096>(a, st);
+    return cudaErrorInvalidValue;
 }
 
 bool xpass4_supported(int sx) {

@@ -115,6 +115,12 @@ CASES = {
     "kpz3d_128x16x16_det": dict(shape=(128, 16, 16), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0), ("iqzh", 0)], params=dict(l=0.5),
                                 eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2 + l*iqzh^2", "iqxh = iqx*h", "iqyh = iqy*h", "iqzh = iqz*h"],
                                 ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
+    "kpz3d_1024x16x8_det": dict(shape=(1024, 16, 8), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0), ("iqzh", 0)], params=dict(l=0.5),
+                                eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2 + l*iqzh^2", "iqxh = iqx*h", "iqyh = iqy*h", "iqzh = iqz*h"],
+                                ic=dict(h=("smooth", (1.0, 0.1))), steps=30),
+    "kpz2d_256x32_mixed_powers": dict(shape=(256, 32, 1), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0)], params=dict(l=0.5, m=0.25),
+                                      eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + m*iqyh^3", "iqxh = iqx*h", "iqyh = iqy*h"],
+                                      ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
     "kpz2d_512x16_mixed_powers": dict(shape=(512, 16, 1), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0)], params=dict(l=0.5, m=0.25),
                                       eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + m*iqyh^3", "iqxh = iqx*h", "iqyh = iqy*h"],
                                       ic=dict(h=("smooth", (1.0, 0.1))), steps=50),
