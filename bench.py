@@ -76,6 +76,7 @@ class ClockSampler:
         self.index, self.proc, self.lines, self.period = index, None, [], period_s
         self.nv, self.handle, self.thread, self.run = None, None, None, False
         self.sm, self.mx, self.reasons = [], [], set()
+        self.samples = []   # (perf_counter, sm_mhz, reason bits): filtered to the timed window in stop()
 
     def _nvml_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
@@ -111,11 +112,9 @@ class ClockSampler:
                 (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
         while self.run:
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                for b, nm in bits:
-                    if r & b:
-                        self.reasons.add(nm)
+                self.samples.append((time.perf_counter(), mhz, tuple(nm for b, nm in bits if r & b)))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -124,10 +123,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.nv is not None:
             self.run = False
             self.thread.join(timeout=1.0)
+            inside = [x for x in self.samples if (t_begin is None or x[0] >= t_begin) and (t_end is None or x[0] <= t_end)]
+            for _, mhz, rs in (inside or self.samples):
+                self.sm.append(mhz)
+                self.reasons.update(rs)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
                     "reasons": sorted(self.reasons), "samples": len(self.sm), "source": f"nvml, polled every {self.period * 1e3:.0f} ms inside the timed region"}
         if not self.proc:
@@ -257,13 +260,17 @@ def main():
     # ---- warm-up (graph capture happens here), then K timed steps; inputs (4 arrays x 0.55 GB) exceed L2
     ev.advanceTime(max(3, args.warmup))
     ev.sync()
-    barrier()
+    # the sampler thread (NVML start-up takes milliseconds) is started BEFORE the barrier: every rank must enter the timed
+    # loop at the same moment, or the late rank's delay is charged to its peers at the first exchange (max over ranks)
     sampler = ClockSampler(local, args.clock_period_ms * 1e-3)
     if rank == 0:
         sampler.start()
-    ms = ev.timeSteps(args.steps)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_begin = time.perf_counter()
+    ms = ev.timeSteps(args.steps)
+    t_end = time.perf_counter()
+    barrier()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     if dist is not None:
         tt = torch.tensor([ms], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
