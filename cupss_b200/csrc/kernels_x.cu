@@ -391,7 +391,7 @@ static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
         fast = a.mono[m].nfac >= 1 && a.mono[m].nfac <= 4;
         for (int f = 1; f < a.mono[m].nfac && fast; ++f) fast = a.mono[m].fac[f] == a.mono[m].fac[0];
     }
-    if (fast && a.tw3 && xpass3_supported(SX) && a.nMono == 1 && (a.mono[0].nfac == 2 || a.mono[0].nfac == 3)) return launch_xpass3(SX, a, st);
+    if (fast && a.tw3 && xpass3_supported(SX) && a.nIn == 1 && a.nMono <= 2) return launch_xpass3(SX, a, st);   // powers 1..4 of the one input
     if (fast && a.nIn > 1 && a.tw3 && xpass3_sumpow_supported(SX) && a.nMono == a.nIn) {
         bool oneEach = true;   // monomial g is a power of input g: the accumulation order of the generic kernels is the input order
         for (int m = 0; m < a.nMono; ++m) oneEach = oneEach && a.mono[m].fac[0] == m;

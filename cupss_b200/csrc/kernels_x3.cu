@@ -33,7 +33,9 @@ template <int SX, int NT> struct X3Cfg {
 template <int SX>
 __device__ __forceinline__ unsigned x3pad(unsigned idx) { return idx + 2u * (idx / (unsigned)X3Cfg<SX, 256>::R1); }
 
-template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS>
+// POLY: the real-space stage is c0*r^p0 + c1*r^p1 of the one input (powers up to 4, c1 = 0 for a single monomial) instead of
+// the straight-line c*r^2 / c*r^3 of the headline class.
+template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS, bool POLY = false>
 __global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant__ XArgs a) {
     using Cfg = X3Cfg<SX, NT>;
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1, M = Cfg::M, TL = Cfg::TL, LB = Cfg::LB, H = R0 / 2;
@@ -114,7 +116,20 @@ __global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant_
         const float2 norm2 = make_float2(a.norm, a.norm);
         const float2 c02 = make_float2(a.mono[0].coef, a.mono[0].coef);
         const bool cube = a.mono[0].nfac == 3;   // the launcher only sends single monomials c*r^2 / c*r^3 here (warp-uniform)
-        if (cube) {
+        if constexpr (POLY) {
+            const int p0 = a.mono[0].nfac, p1 = a.nMono > 1 ? a.mono[1].nfac : 0;   // warp-uniform
+            const float c1 = a.nMono > 1 ? a.mono[1].coef : 0.0f;
+            const float2 c12 = make_float2(c1, c1);
+#pragma unroll
+            for (int i = 0; i < R1; ++i) {
+                const float2 r = cmul2(y[i], norm2);
+                const float2 r2 = cmul2(r, r), r3 = cmul2(r2, r), r4 = cmul2(r3, r);
+                const float2 one = make_float2(1.0f, 1.0f);
+                const float2 w0 = p0 == 1 ? r : (p0 == 2 ? r2 : (p0 == 3 ? r3 : r4));
+                const float2 w1 = p1 == 0 ? one : (p1 == 1 ? r : (p1 == 2 ? r2 : (p1 == 3 ? r3 : r4)));
+                y[i] = cadd(cmul2(c02, w0), cmul2(c12, w1));
+            }
+        } else if (cube) {
 #pragma unroll
             for (int i = 0; i < R1; ++i) {
                 const float2 r = cmul2(y[i], norm2);
@@ -320,20 +335,20 @@ __global__ void __launch_bounds__(128, 3) xpass3s_kernel(const __grid_constant__
     if (t0) emit(SX / 2, xA[H], xA[H]);
 }
 
-template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS>
+template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS, bool POLY = false>
 static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
     using Cfg = X3Cfg<SX, NT>;
     static bool attr = false;
     if (!attr) {
         if (Cfg::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT, MINB, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const long long njobs = (a.nlines + 1) / 2;
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
-    xpass3_kernel<SX, NT, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    xpass3_kernel<SX, NT, MINB, POLY><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -371,6 +386,12 @@ bool xpass3_supported(int sx) { return sx == 512 || sx == 128 || xpass4_supporte
 
 cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st) {
     if (xpass4_supported(sx)) return launch_xpass4(sx, a, st);   // long lines: the three-level kernel (kernels_x4.cu)
+    const bool straight = a.nMono == 1 && (a.mono[0].nfac == 2 || a.mono[0].nfac == 3);
+    if (!straight) {   // two monomials / other powers of the one input
+        if (sx == 512) return launch_x3_size<512, 128, 4, true>(a, st);
+        if (sx == 128) return launch_x3_size<128, 256, 2, true>(a, st);
+        return cudaErrorInvalidValue;
+    }
     static const int nt = [] { const char* e = getenv("CUPSS_B200_X3_THREADS"); return e ? atoi(e) : 128; }();   // measured (profiles/README.md): 0.202 ms at 128, 0.208 at 64, 0.229 at 256
     if (sx == 512) return nt == 256 ? launch_x3_size<512, 256>(a, st) : (nt == 64 ? launch_x3_size<512, 64>(a, st) : launch_x3_size<512, 128>(a, st));
     if (sx == 128) return launch_x3_size<128, 256>(a, st);

@@ -45,7 +45,8 @@ __device__ __forceinline__ void job_sync(unsigned job) {
     else asm volatile("bar.sync %0, %1;" ::"r"(job + 1u), "n"(TJ) : "memory");
 }
 
-template <int SX>
+// POLY: c0*r^p0 + c1*r^p1 of the one input (powers up to 4) instead of the straight-line c*r^2 / c*r^3.
+template <int SX, bool POLY = false>
 __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __grid_constant__ XArgs a) {
     using Cfg = X4Cfg<SX>;
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1, R2 = Cfg::R2, M = Cfg::M0, N1 = Cfg::N1, M1 = Cfg::M1, TJ = Cfg::TJ, LB = Cfg::LB, H = R0 / 2;
@@ -142,7 +143,19 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
                 y[2 * i] = make_float2(v.x, v.y); y[2 * i + 1] = make_float2(v.z, v.w);
             }
             Dft<R2, +1>::run(y);
-            if (cube) {
+            if constexpr (POLY) {
+                const int p0 = a.mono[0].nfac, p1 = a.nMono > 1 ? a.mono[1].nfac : 0;   // warp-uniform
+                const float c1 = a.nMono > 1 ? a.mono[1].coef : 0.0f;
+                const float2 c12 = make_float2(c1, c1), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+                for (int i = 0; i < R2; ++i) {
+                    const float2 r = cmul2(y[i], norm2);
+                    const float2 r2 = cmul2(r, r), r3 = cmul2(r2, r), r4 = cmul2(r3, r);
+                    const float2 w0 = p0 == 1 ? r : (p0 == 2 ? r2 : (p0 == 3 ? r3 : r4));
+                    const float2 w1 = p1 == 0 ? one : (p1 == 1 ? r : (p1 == 2 ? r2 : (p1 == 3 ? r3 : r4)));
+                    y[i] = cadd(cmul2(c02, w0), cmul2(c12, w1));
+                }
+            } else if (cube) {
 #pragma unroll
                 for (int i = 0; i < R2; ++i) {
                     const float2 r = cmul2(y[i], norm2);
@@ -402,20 +415,20 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 3) xpass4s_kernel(const __
     }
 }
 
-template <int SX>
+template <int SX, bool POLY = false>
 static cudaError_t launch_x4_size(XArgs& a, cudaStream_t st) {
     using Cfg = X4Cfg<SX>;
     static bool attr = false;
     if (!attr) {
         if (Cfg::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xpass4_kernel<SX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(xpass4_kernel<SX, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const long long njobs = (a.nlines + 1) / 2;
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
-    xpass4_kernel<SX><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    xpass4_kernel<SX, POLY><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -451,6 +464,14 @@ bool xpass4_supported(int sx) {
 }
 
 cudaError_t launch_xpass4(int sx, XArgs& a, cudaStream_t st) {
+    const bool straight = a.nMono == 1 && (a.mono[0].nfac == 2 || a.mono[0].nfac == 3);
+    if (!straight) {   // two monomials / other powers of the one input
+        if (sx == 256) return launch_x4_size<256, true>(a, st);
+        if (sx == 1024) return launch_x4_size<1024, true>(a, st);
+        if (sx == 2048) return launch_x4_size<2048, true>(a, st);
+        if (sx == 4096) return launch_x4_size<4096, true>(a, st);
+        return cudaErrorInvalidValue;
+    }
     if (sx == 256) return launch_x4_size<256>(a, st);
     if (sx == 1024) return launch_x4_size<1024>(a, st);
     if (sx == 2048) return launch_x4_size<2048>(a, st);

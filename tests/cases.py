@@ -75,6 +75,15 @@ CASES = {
                           ic=dict(phi=("smooth", (0.5, 0.05))), steps=50),
     "burgers1d_2048": dict(shape=(2048, 1, 1), dt=0.01, fields=[("u", 1)], params=dict(nu=0.5), eqs=["dt u + nu*q^2*u = -0.5*iqx*u^2"],
                            ic=dict(u=("smooth", (0.5, 0.05))), steps=100),
+    # two monomials / other powers of ONE input through the specialised x kernels (Swift-Hohenberg-like quadratic + cubic, quartic)
+    "sh2d_512x16_two_monomials": dict(shape=(512, 16, 1), dt=0.02, fields=[("u", 1)], params=dict(r=0.3, g=0.8),
+                                      eqs=["dt u + (1 - 2*q^2 + q^4 - r)*u = g*u^2 - u^3"], ic=dict(u=("smooth", (0.5, 0.05))), steps=60),
+    "sh3d_256x16x8_two_monomials": dict(shape=(256, 16, 8), dt=0.02, fields=[("u", 1)], params=dict(r=0.3, g=0.8),
+                                        eqs=["dt u + (1 - 2*q^2 + q^4 - r)*u = g*u^2 - u^3"], ic=dict(u=("smooth", (0.5, 0.05))), steps=40),
+    "quartic2d_1024x16": dict(shape=(1024, 16, 1), dt=0.02, fields=[("u", 1)], params=dict(c=0.5), eqs=["dt u + q^2*u = - c*q^2*u^4"],
+                              ic=dict(u=("smooth", (0.5, 0.05))), steps=60),
+    "quartic1d_128": dict(shape=(128, 1, 1), dt=0.02, fields=[("u", 1)], params=dict(c=0.5), eqs=["dt u + q^2*u = - c*q^2*u^4 + 0.25*q^2*u^2"],
+                          ic=dict(u=("smooth", (0.5, 0.05))), steps=60),
     # quadratic nonlinearity through the same kernel (single monomial c*r^2)
     "burgers_like_128": dict(shape=(128, 32, 1), dt=0.01, fields=[("u", 1)], params=dict(nu=0.5), eqs=["dt u + nu*q^2*u = -0.5*iqx*u^2"],
                              ic=dict(u=("smooth", (0.5, 0.05))), steps=100),

@@ -62,7 +62,7 @@ def test_reference_unit_tests_operators(built, dim, flavour):
     assert max(errs.values()) < refcases.TOL, errs
 
 
-@pytest.mark.parametrize("name", ["diffusion2d_256", "ch2d_64", "ch2d_64_cpu_rule", "ch3d_32", "ch3d_64x32x16", "ch3d_128x16x16", "ch2d_512x16", "ch3d_512x8x8", "burgers_like_128",
+@pytest.mark.parametrize("name", ["diffusion2d_256", "ch2d_64", "ch2d_64_cpu_rule", "ch3d_32", "ch3d_64x32x16", "ch3d_128x16x16", "ch2d_512x16", "ch3d_512x8x8", "burgers_like_128", "sh2d_512x16_two_monomials", "sh3d_256x16x8_two_monomials", "quartic2d_1024x16", "quartic1d_128",
                                   "ch3d_256x16x8", "ch2d_1024x32", "ch2d_2048x32", "ch2d_4096x32", "ch3d_1024x32x8", "burgers1d_2048",
                                   "modelh_32", "kpz3d_32_det", "kpz3d_128x16x16_det", "kpz2d_512x16_mixed_powers", "kpz3d_1024x16x8_det", "kpz2d_256x32_mixed_powers", "ops1d_16", "ops3d_16", "bc_even_inhomogeneous_64", "bc_odd_diffusion_64",
                                   "fcb_lowpass_ch2d_64", "fcb_asym_ch3d_16", "fcb_constraint_kpz2d_32", "fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64"])
