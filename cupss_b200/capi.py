@@ -54,6 +54,8 @@ _SIGS = {
     "cupss_capi_initialize_from_file": (None, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char]),
     "cupss_capi_dump_plan": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "cupss_capi_set_mirror_callback": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "cupss_capi_print_information": (None, [C.c_void_p]),
+    "cupss_capi_copy_host_to_device": (None, [C.c_void_p, C.c_char_p]),
     "cupss_capi_set_fourier_callback": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
 }
 
@@ -61,6 +63,7 @@ _SIGS = {
 _PRODUCT_SIGS = {
     "cupss_capi_engine_plan": (C.c_void_p, [C.c_void_p]),
     "cupss_capi_set_noise_seed": (None, [C.c_void_p, C.c_ulonglong]),
+    "cupss_capi_get_noise_seed": (C.c_ulonglong, [C.c_void_p]),
     "cupss_capi_set_partition": (None, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
 }
 
@@ -183,6 +186,9 @@ class Evolver:
 
     def setNoiseSeed(self, seed: int):
         self._lib.cupss_capi_set_noise_seed(self._h, int(seed))
+
+    def getNoiseSeed(self) -> int:
+        return int(self._lib.cupss_capi_get_noise_seed(self._h))
 
     def setPartition(self, rank: int, nranks: int, nccl_id: bytes):
         self._lib.cupss_capi_set_partition(self._h, int(rank), int(nranks), nccl_id)
@@ -308,10 +314,18 @@ class Evolver:
     def initializeFromFile(self, name, path, skiprows=1, delimiter=","):
         self._lib.cupss_capi_initialize_from_file(self._h, name.encode(), path.encode(), skiprows, delimiter.encode())
 
-    def setMirrorCallback(self, name: str, odd: bool = False):
-        """Install the facade's built-in host callback (mirror boundary condition) on a field of a RUN_CPU evolver."""
-        if self._lib.cupss_capi_set_mirror_callback(self._h, name.encode(), 1 if odd else 0) != 0:
+    def setMirrorCallback(self, name: str, odd=False):
+        """Install one of the facade's built-in host callbacks on a field of a RUN_CPU evolver: False / True = even / odd
+        mirror boundary condition, 2 = the non-symmetric strip clamp (tools/cupss_capi.cpp)."""
+        if self._lib.cupss_capi_set_mirror_callback(self._h, name.encode(), int(odd)) != 0:
             raise KeyError(name)
+
+    def printInformation(self):
+        self._lib.cupss_capi_print_information(self._h)
+
+    def copyHostToDevice(self, name: str):
+        """field::copyHostToDevice: push the (edited) host real array of a field to the device mid-run."""
+        self._lib.cupss_capi_copy_host_to_device(self._h, name.encode())
 
     def setFourierCallback(self, name: str, kind: int = 0, device_flavour: bool = False):
         """Install one of the facade's built-in Fourier-space callbacks (field::callbackFourier; tools/cupss_capi.cpp)."""

@@ -259,6 +259,7 @@ struct Field {
     float2* S = nullptr;    // spectrum
     float2* W2 = nullptr;   // dealiased field, y-inverse done
     int w2cut[3] = {-1, -1, -1};   // cut-offs W2 was pruned with (pruned regions rely on staying zero)
+    bool w2FullBand = false;       // a real-space callback wrote W2: the x pass must not stop at the dealias cut-off
 };
 
 struct Launch {
@@ -315,6 +316,9 @@ struct cupss_b200_plan {
     float2* peerArena[CUPSS_MAX_PEERS] = {nullptr};
     static constexpr size_t kArenaHeader = 4096;   // float2 elements (32 KiB)
     int arenaNext = 0, nextPt = 0;
+    int* hostErr = nullptr;       // mapped page-locked word raised by a barrier that timed out (kernels_axis.cu)
+    int* hostErrDev = nullptr;
+    unsigned long long barrierTimeoutNs = 60ull * 1000000000ull;   // CUPSS_B200_BARRIER_TIMEOUT_S (0: wait for ever)
 
     // ------------------------------------------------------------ helpers
     int get_twiddle(int L, const float2** out) {
@@ -455,6 +459,8 @@ struct cupss_b200_plan {
         for (int d = 0; d < CUPSS_MAX_PEERS; ++d) l.xb.flags[d] = d < nranks ? reinterpret_cast<unsigned int*>(peerArena[d]) : nullptr;
         l.xb.epoch = arena ? reinterpret_cast<unsigned int*>(arena) + 1024 : nullptr;
         l.xb.error = arena ? reinterpret_cast<int*>(arena) + 2048 : nullptr;
+        l.xb.hostError = hostErrDev;
+        l.xb.timeoutNs = barrierTimeoutNs;
         l.xb.rank = rank; l.xb.nranks = nranks; l.xb.pt = nextPt++;
         out.push_back(l);
     }
@@ -744,7 +750,7 @@ struct cupss_b200_plan {
                 x.xa.in[i] = F.W2;
                 short cx, cy, cz;
                 cutoffs(F.aliasOrder, &cx, &cy, &cz);
-                x.xa.kmax[i] = prune ? (cx < ncol - 1 ? cx : ncol - 1) : ncol - 1;
+                x.xa.kmax[i] = (prune && !F.w2FullBand) ? (cx < ncol - 1 ? cx : ncol - 1) : ncol - 1;
                 inFrac += (double)(x.xa.kmax[i] + 1) / ncol;
             }
             x.xa.nOut = (int)(g1 - g0);
@@ -1089,8 +1095,8 @@ struct cupss_b200_plan {
         return CUPSS_B200_OK;
     }
     // Real view of a field for a callback: which = 0 the field itself, 1 its dealiased copy (what products read).
+    // Partitioned plans: the view is this rank's z-slab [zl][sy][sx] (collective for which == 0: the full transform exchanges slabs).
     int view_begin(int f, int which, float2** dev) {
-        if (nranks != 1) return fail(CUPSS_B200_ERR_ARG, "user callbacks are single-GPU only");
         Field& F = fields[f];
         const size_t n = (size_t)sx * sy * zl;
         if (!realBuf) CK(cudaMalloc(&realBuf, n * sizeof(float)));
@@ -1102,7 +1108,11 @@ struct cupss_b200_plan {
             if (!F.W2) return fail(CUPSS_B200_ERR_STATE, "field %s has no dealiased copy", F.name.c_str());
             Launch x{};
             x.kind = Launch::XPASS; x.mode = X_C2R_ONLY;
-            x.xa.nIn = 1; x.xa.in[0] = F.W2; x.xa.kmax[0] = ncol - 1;
+            // the fresh dealiased copy is band-limited; column tiles beyond the cut-off are never rewritten by the pruned inverse
+            // passes and may still hold what an earlier callback commit left there
+            short cx, cy, cz;
+            cutoffs(F.aliasOrder, &cx, &cy, &cz);
+            x.xa.nIn = 1; x.xa.in[0] = F.W2; x.xa.kmax[0] = prune ? (cx < ncol - 1 ? cx : ncol - 1) : ncol - 1;
             x.xa.pitch = pitch; x.xa.nlines = (long long)zl * sy;
             x.xa.norm = 1.0f / ((float)sx * (float)sy * (float)sz);
             x.xa.realOut = realBuf;
@@ -1131,6 +1141,17 @@ struct cupss_b200_plan {
             x.xa.realIn = realBuf;
             CKR(get_twiddle(sx, &x.xa.tw));
             CKR(run_launch(x));
+            // What the callback left in the dealiased copy is not band-limited in x any more, and the reference feeds it to
+            // computeProduct unchanged (src/field.cpp:75-83, src/term.cpp:85-92): from now on the hot x pass loads the full
+            // band of this field instead of stopping at the dealias cut-off.
+            if (!F.w2FullBand) {
+                F.w2FullBand = true;
+                for (Launch& l : step)
+                    if (l.kind == Launch::XPASS)
+                        for (int i = 0; i < l.xa.nIn; ++i)
+                            if (l.xa.in[i] == F.W2) l.xa.kmax[i] = ncol - 1;
+                drop_graph();
+            }
         }
         return CUPSS_B200_OK;
     }
@@ -1144,7 +1165,7 @@ struct cupss_b200_plan {
         Field& F = fields[f];
         if (!F.S) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
         if (!viewBuf) CK(cudaMalloc(&viewBuf, (size_t)sx * sy * zl * sizeof(float2)));
-        CK(launch_spectrum_expand(F.S, viewBuf, sx, sy, sz, pitch, stream));
+        CK(launch_spectrum_expand(F.S, viewBuf, sx, sy, sz, pitch, sy, 0, sz, stream));
         CK(cudaStreamSynchronize(stream));
         *dev = viewBuf;
         return CUPSS_B200_OK;
@@ -1222,6 +1243,7 @@ void cupss_b200_destroy(cupss_b200_plan* p) {
     for (int d = 0; d < p->nranks; ++d)
         if (d != p->rank && p->peerArena[d]) cudaIpcCloseMemHandle(p->peerArena[d]);
     if (p->arena) cudaFree(p->arena);
+    if (p->hostErr) cudaFreeHost(p->hostErr);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1251,7 +1273,23 @@ int cupss_b200_set_partition(cupss_b200_plan* p, int rank, int nranks, const voi
     p->useP2P = !(na && na[0] == '1');
     p->zl = p->sz / nranks; p->kyl = p->sy / nranks;
     p->specElems = (size_t)p->pitch * p->kyl * p->sz;   // == pitch * sy * zl
+    if (!p->hostErr) {
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&p->hostErr), sizeof(int), cudaHostAllocMapped));
+        *p->hostErr = 0;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p->hostErrDev), p->hostErr, 0));
+    }
+    if (const char* to = getenv("CUPSS_B200_BARRIER_TIMEOUT_S")) p->barrierTimeoutNs = (unsigned long long)(atof(to) * 1e9);
     return CUPSS_B200_OK;
+}
+
+// A cross-GPU barrier that timed out has trapped: every later CUDA call on this context fails with a generic launch error.
+// Entry points that run or consume steps pass their status through here so that the caller sees the actual cause, and a
+// time-out is reported even when the failing call itself was not the one that noticed.
+static int comm_guard(cupss_b200_plan* p, int rc) {
+    if (p && p->hostErr && *reinterpret_cast<volatile int*>(p->hostErr))
+        return fail(CUPSS_B200_ERR_COMM, "cross-GPU barrier timed out after %.0f s (a peer rank stopped or fell behind; CUPSS_B200_BARRIER_TIMEOUT_S): "
+                                         "the step was aborted before it could read stale receive slots", (double)p->barrierTimeoutNs * 1e-9);
+    return rc;
 }
 
 int cupss_b200_add_field(cupss_b200_plan* p, const char* name, int dynamic) {
@@ -1345,7 +1383,7 @@ int cupss_b200_upload_real(cupss_b200_plan* p, int f, const float* host) {
     return CUPSS_B200_OK;
 }
 
-int cupss_b200_download_real(cupss_b200_plan* p, int f, float* host) {
+static int download_real_impl(cupss_b200_plan* p, int f, float* host) {
     CKR(check_field(p, f));
     Field& F = p->fields[f];
     if (!F.S || !host) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
@@ -1358,23 +1396,42 @@ int cupss_b200_download_real(cupss_b200_plan* p, int f, float* host) {
     CK(cudaStreamSynchronize(p->stream));
     return CUPSS_B200_OK;
 }
+int cupss_b200_download_real(cupss_b200_plan* p, int f, float* host) {
+    if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
+    return comm_guard(p, download_real_impl(p, f, host));
+}
 
-int cupss_b200_download_comp(cupss_b200_plan* p, int f, float* host) {
+// Full spectrum float2[.][sy][sx] of the reference's comp_array (src/evolver.cpp:364-368 copies it next to the real array).
+// Partitioned plans (collective: every rank calls it): the ky-slabs of all ranks are all-gathered and each rank expands the
+// kz planes of its own z-slab, so `host` receives [zl][sy][sx] -- the same slab convention as upload_real / download_real.
+static int download_comp_impl(cupss_b200_plan* p, int f, float* host) {
     CKR(check_field(p, f));
     Field& F = p->fields[f];
     if (!F.S || !host) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
-    if (p->nranks != 1) return fail(CUPSS_B200_ERR_ARG, "download_comp is single-rank only");
     CKR(ensure_view_buf(p));
-    const size_t n = (size_t)p->sx * p->sy * p->sz;
-    CK(launch_spectrum_expand(F.S, p->viewBuf, p->sx, p->sy, p->sz, p->pitch, p->stream));
+    const size_t n = (size_t)p->sx * p->sy * p->zl;
+    float2* all = nullptr;
+    const float2* half = F.S;
+    if (p->nranks > 1) {
+        CK(cudaMalloc(&all, (size_t)p->nranks * p->specElems * sizeof(float2)));
+        NK(g_nccl.AllGather(F.S, all, p->specElems * 2, /*ncclFloat*/ 7, p->comm, p->stream));
+        half = all;
+    }
+    CK(launch_spectrum_expand(half, p->viewBuf, p->sx, p->sy, p->sz, p->pitch, p->kyl, p->rank * p->zl, p->zl, p->stream));
     CK(cudaMemcpyAsync(host, p->viewBuf, n * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if (all) CK(cudaFree(all));
     return CUPSS_B200_OK;
+}
+int cupss_b200_download_comp(cupss_b200_plan* p, int f, float* host) {
+    if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
+    return comm_guard(p, download_comp_impl(p, f, host));
 }
 
 int cupss_b200_step(cupss_b200_plan* p, int nsteps) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
-    return p->do_steps(nsteps);
+    CKR(comm_guard(p, CUPSS_B200_OK));   // a time-out of an earlier (asynchronous) step
+    return comm_guard(p, p->do_steps(nsteps));
 }
 int cupss_b200_jit_selftest(char* log, int loglen) {
     // Compiles (does not load) the plan-specialised k stage of a synthetic Model-H-like sweep with NVRTC: keeps the kernel
@@ -1403,7 +1460,8 @@ int cupss_b200_jit_selftest(char* log, int loglen) {
 
 int cupss_b200_step_stage(cupss_b200_plan* p, int stage) {
     if (!p || stage < 0 || stage > 1) return fail(CUPSS_B200_ERR_ARG, "bad stage");
-    return p->do_stage(stage);
+    CKR(comm_guard(p, CUPSS_B200_OK));
+    return comm_guard(p, p->do_stage(stage));
 }
 int cupss_b200_real_view_begin(cupss_b200_plan* p, int f, int which, void** dev_float2) {
     CKR(check_field(p, f));
@@ -1426,15 +1484,13 @@ int cupss_b200_comp_view_commit(cupss_b200_plan* p, int f) {
     CKR(check_field(p, f));
     return p->comp_view_commit(f);
 }
+static int sync_impl(cupss_b200_plan* p) {
+    CK(cudaStreamSynchronize(p->stream));
+    return CUPSS_B200_OK;
+}
 int cupss_b200_sync(cupss_b200_plan* p) {
     if (!p) return fail(CUPSS_B200_ERR_ARG, "null plan");
-    CK(cudaStreamSynchronize(p->stream));
-    if (p->arena) {
-        int err = 0;
-        CK(cudaMemcpy(&err, reinterpret_cast<int*>(p->arena) + 2048, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) return fail(CUPSS_B200_ERR_COMM, "cross-GPU barrier timed out (a peer rank stopped)");
-    }
-    return CUPSS_B200_OK;
+    return comm_guard(p, sync_impl(p));
 }
 
 int cupss_b200_field_alias(cupss_b200_plan* p, int f, int* needs, int* order) {
@@ -1450,9 +1506,9 @@ int cupss_b200_time_steps(cupss_b200_plan* p, int nsteps, float* ms) {
     CK(cudaEventRecord(p->ev0, p->stream));
     CKR(p->do_steps(nsteps));
     CK(cudaEventRecord(p->ev1, p->stream));
-    CK(cudaEventSynchronize(p->ev1));
+    if (cudaEventSynchronize(p->ev1) != cudaSuccess) return comm_guard(p, fail(CUPSS_B200_ERR_CUDA, "the timed steps failed: %s", cudaGetErrorString(cudaGetLastError())));
     CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
-    return CUPSS_B200_OK;
+    return comm_guard(p, CUPSS_B200_OK);
 }
 
 int cupss_b200_profile_step(cupss_b200_plan* p, int nmax, char* names, float* ms, double* bytes, int* n) {

@@ -52,6 +52,8 @@ struct XBarrier {
     unsigned int* flags[CUPSS_MAX_PEERS];   // base of each peer's flag table [pt][CUPSS_MAX_PEERS]
     unsigned int* epoch;                    // local epoch counters [pt]
     int* error;                             // local: set to 1 on timeout
+    int* hostError;                         // the same word in mapped page-locked host memory: readable after the trap
+    unsigned long long timeoutNs;           // 0: wait for ever
     int rank, nranks, pt;
 };
 
@@ -97,8 +99,9 @@ cudaError_t launch_bump_counter(unsigned int* counter, cudaStream_t st);
 cudaError_t launch_spectrum_compress(const float2* full, float2* half, int sx, int sy, int sz, int pitch, cudaStream_t st);
 cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStream_t st);
 cudaError_t launch_real_compress(const float2* in, float* out, size_t n, cudaStream_t st);
-// Hermitian half spectrum [sz][sy][pitch] -> full spectrum float2[sz][sy][sx] (comp_array layout of the reference)
-cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, cudaStream_t st);
+// Hermitian half spectrum -> planes [z0, z0 + zl) of the full spectrum float2[sz][sy][sx] (comp_array layout of the reference).
+// `half` is [src][sz][kyl][pitch] with src = ky / kyl: one rank's array when kyl == sy, the all-gathered ky-slabs otherwise.
+cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, cudaStream_t st);
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
 // Launch geometry of the k-stage kernel for length L (for kernels compiled at run time)

@@ -19,6 +19,15 @@ namespace cupss {
 
 __global__ void bump_counter_kernel(unsigned int* c) { *c += 1u; }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// A peer that never arrives (dead process, a rank stuck for longer than the time-out in host code) must not let the step
+// run on with stale or half-written receive slots: the error word is raised in device AND mapped host memory and the
+// kernel traps, which fails every later call on this context -- the engine reports the time-out (engine.cu: comm_guard).
 __global__ void xgpu_barrier_kernel(const XBarrier b) {
     __shared__ unsigned int target;
     if (threadIdx.x == 0) {
@@ -33,12 +42,18 @@ __global__ void xgpu_barrier_kernel(const XBarrier b) {
         unsigned int* theirs = b.flags[d] + b.pt * CUPSS_MAX_PEERS + b.rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(target) : "memory");
         const unsigned int* mine = b.flags[b.rank] + b.pt * CUPSS_MAX_PEERS + d;
-        const long long t0 = clock64();
-        unsigned int seen;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int seen, spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-            if (clock64() - t0 > 6000000000LL) { *b.error = 1; break; }   // ~3 s: a peer died; do not hang the GPU
-        } while ((int)(seen - target) < 0);
+            if ((int)(seen - target) >= 0) break;
+            if ((++spins & 1023u) == 0u && b.timeoutNs && global_timer_ns() - t0 > b.timeoutNs) {
+                *b.error = 1;
+                if (b.hostError) *reinterpret_cast<volatile int*>(b.hostError) = 1;
+                __threadfence_system();
+                __trap();
+            }
+        } while (true);
         __threadfence_system();
     }
 }
@@ -172,25 +187,28 @@ __global__ void real_expand_kernel(const float* __restrict__ in, float2* __restr
 __global__ void real_compress_kernel(const float2* __restrict__ in, float* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i].x;
 }
-__global__ void spectrum_expand_kernel(const float2* __restrict__ half, float2* __restrict__ full, int sx, int sy, int sz, int pitch) {
-    const size_t n = (size_t)sx * sy * sz;
+__global__ void spectrum_expand_kernel(const float2* __restrict__ half, float2* __restrict__ full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl) {
+    const size_t n = (size_t)sx * sy * zl;
+    auto at = [&](int k, int j, int i) -> float2 {   // [src = j / kyl][k][j % kyl][i]
+        const int src = j / kyl, jl = j - src * kyl;
+        return half[(((size_t)src * sz + k) * kyl + jl) * pitch + i];
+    };
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(o % sx);
         const size_t r = o / sx;
-        const int j = (int)(r % sy), k = (int)(r / sy);
+        const int j = (int)(r % sy), k = z0 + (int)(r / sy);
         float2 v;
         if (i <= sx / 2) {
-            v = half[((size_t)k * sy + j) * pitch + i];
+            v = at(k, j, i);
         } else {   // X(k) = conj X(-k)
-            const int mk = (sz - k) % sz, mj = (sy - j) % sy;
-            v = half[((size_t)mk * sy + mj) * pitch + (sx - i)];
+            v = at((sz - k) % sz, (sy - j) % sy, sx - i);
             v.y = -v.y;
         }
         full[o] = v;
     }
 }
-cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, cudaStream_t st) {
-    spectrum_expand_kernel<<<148 * 8, 256, 0, st>>>(half, full, sx, sy, sz, pitch);
+cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, cudaStream_t st) {
+    spectrum_expand_kernel<<<148 * 8, 256, 0, st>>>(half, full, sx, sy, sz, pitch, kyl, z0, zl);
     return cudaGetLastError();
 }
 // Hermitian part of a full spectrum, stored as the half spectrum: H(k) = (F(k) + conj F(-k)) / 2 for kx <= sx/2.

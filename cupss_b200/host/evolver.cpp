@@ -174,7 +174,20 @@ void evolver::setOutputField(const std::string &name, int on) {
 
 // Everything the parser produced goes to the engine in one go; finalize builds the fused schedule.
 void evolver::sendSystemToEngine() {
-    if (!seedFixed) { noiseSeed = (unsigned long long)time(NULL); seedFixed = true; }   // the reference seeds from time(NULL)
+    if (!seedFixed) {
+        // The reference seeds from time(NULL).  The Philox stream is keyed on (global mode, field, step, seed) and must be the
+        // same on every rank of a partitioned run (conjugate partner rows of the kx = 0 and kx = sx/2 planes live on different
+        // ranks): there the default seed is a hash of the 128-byte NCCL unique id, which all ranks share and which differs
+        // from run to run; ranks starting in different seconds would otherwise disagree.
+        if (partRanks > 1) {
+            unsigned long long h = 1469598103934665603ull;   // FNV-1a
+            for (int i = 0; i < 128; ++i) { h ^= (unsigned char)partId[i]; h *= 1099511628211ull; }
+            noiseSeed = h;
+        } else {
+            noiseSeed = (unsigned long long)time(NULL);
+        }
+        seedFixed = true;
+    }
     for (field *f : fields) {
         std::vector<cupss_b200_pres> imp;
         for (const pres &p : f->implicit) imp.push_back({p.preFactor, p.q2n, p.iqx, p.iqy, p.iqz, p.invq});
@@ -246,8 +259,8 @@ void evolver::prepareProblem() {
     if (verbose) std::cout << "Building the fused per-equation plan." << std::endl;
     sendSystemToEngine();
     for (field *f : fields) {
-        if ((f->hasCB || f->hasCBFourier) && partRanks > 1) {
-            std::cout << "ERROR: user callbacks (field " << f->name << ") need a single-GPU run" << std::endl;
+        if (f->hasCBFourier && partRanks > 1) {
+            std::cout << "ERROR: Fourier-space callbacks (field " << f->name << ") need a single-GPU run" << std::endl;
             std::exit(1);
         }
         f->system_p = this;
@@ -262,18 +275,21 @@ void evolver::applyCallback(field *f) {
         std::cout << "Wants to apply callback function but pointer to function is NULL" << std::endl;
         return;
     }
-    const size_t n = (size_t)sx * sy * sz;
+    // partitioned run: the callback sees this rank's z-slab, float2[sz/P][sy][sx], and is told so through its sz argument
+    const int zl = sz / partRanks;
+    const size_t n = (size_t)sx * sy * zl;
+    const size_t slab = n * (size_t)partRank;
     for (int which = 0; which < (f->needsaliasing ? 2 : 1); ++which) {
         void *dev = nullptr;
         engineCheck(cupss_b200_real_view_begin(plan, f->engine_id, which, &dev), "real_view_begin");
         if (with_cuda) {
-            f->callback(this, static_cast<float2 *>(dev), sx, sy, sz);
+            f->callback(this, static_cast<float2 *>(dev), sx, sy, zl);
         } else {
             std::vector<float2> tmp;
-            float2 *host = f->real_array;
+            float2 *host = f->real_array + slab;
             if (which == 1) { tmp.resize(n); host = tmp.data(); }
             if (cudaMemcpy(host, dev, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) engineCheck(2, "callback download");
-            f->callback(this, host, sx, sy, sz);
+            f->callback(this, host, sx, sy, zl);
             if (cudaMemcpy(dev, host, n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) engineCheck(2, "callback upload");
         }
         engineCheck(cupss_b200_real_view_commit(plan, f->engine_id, which), "real_view_commit");
@@ -331,7 +347,16 @@ void evolver::refreshHostMirror(field *f, bool real_part, bool comp_part) {
     if (!plan || f->engine_id < 0) return;
     const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;
     if (real_part) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array + slab)), "download_real");
-    if (comp_part && partRanks == 1) engineCheck(cupss_b200_download_comp(plan, f->engine_id, reinterpret_cast<float *>(f->comp_array)), "download_comp");
+    // partitioned: collective (every rank calls it); each rank receives the kz planes of its own z-slab of the full spectrum
+    if (comp_part) engineCheck(cupss_b200_download_comp(plan, f->engine_id, reinterpret_cast<float *>(f->comp_array + slab)), "download_comp");
+}
+
+// field::copyHostToDevice / copyRealHostToDevice (src/field.cpp:337-348): the user edited the host real array mid-run and
+// pushes it to the device.  The engine keeps spectra, so the upload is the forward transform of the (slab of the) host array.
+void evolver::uploadHostMirror(field *f) {
+    if (!plan || f->engine_id < 0) return;   // before prepareProblem the host arrays ARE the state
+    const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;
+    engineCheck(cupss_b200_upload_real(plan, f->engine_id, reinterpret_cast<const float *>(f->real_array + slab)), "upload_real");
 }
 
 void evolver::writeOut() {

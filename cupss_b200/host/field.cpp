@@ -62,8 +62,10 @@ float field::getStepqy() { return stepqy; }
 float field::getStepqz() { return stepqz; }
 
 // The engine owns device state; these keep the reference's names for user code that calls them.
-void field::copyHostToDevice() { if (system_p) system_p->markPlanDirty(); }
-void field::copyRealHostToDevice() { if (system_p) system_p->markPlanDirty(); }
+// Mid-run edits of the host real array reach the device through these, as in the reference; the engine keeps the
+// spectrum, so both spell "forward-transform my real array" (the reference's comp_array copy is implied by it).
+void field::copyHostToDevice() { if (system_p) system_p->uploadHostMirror(this); }
+void field::copyRealHostToDevice() { if (system_p) system_p->uploadHostMirror(this); }
 void field::copyDeviceToHost() { if (system_p) system_p->refreshHostMirror(this, true, true); }
 void field::copyRealDeviceToHost() { if (system_p) system_p->refreshHostMirror(this, true, false); }
 void field::prepareDevice() { for (term *t : terms) t->prepareDevice(); }

@@ -80,7 +80,9 @@ class evolver {
     // ---- B200 engine access (additions; not in the reference)
     cupss_b200_plan *enginePlan() { return plan; }
     void setNoiseSeed(unsigned long long seed) { noiseSeed = seed; seedFixed = true; }
+    unsigned long long getNoiseSeed() const { return noiseSeed; }   // valid after prepareProblem (default: time, or a hash shared by all ranks)
     void refreshHostMirror(field *f, bool real_part, bool comp_part);
+    void uploadHostMirror(field *f);   // host real array -> device state (field::copyHostToDevice)
     void markPlanDirty() { planDirty = true; }
     // Slab partition over `nranks` processes (one GPU each); 3-D only.  Host arrays stay full-size, each
     // rank reads/writes only its own z-slab [rank*sz/nranks, (rank+1)*sz/nranks).  Call before prepareProblem.

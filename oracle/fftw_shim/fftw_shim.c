@@ -63,6 +63,10 @@ static int g_double = 1;
 void cupss_shim_set_double(int on) { g_double = on ? 1 : 0; }
 int cupss_shim_get_double(void) { return g_double; }
 
+/* work array of the double-inside mode (the reference's CPU path is single-threaded: one transform at a time) */
+static cpxd *g_work = NULL;
+static size_t g_work_len = 0;
+
 static fftwf_plan make_plan(int rank, const int *n, fftwf_complex *in, fftwf_complex *out, int sign)
 {
     fftwf_plan p = (fftwf_plan)calloc(1, sizeof(*p));
@@ -111,13 +115,28 @@ void fftwf_execute(const fftwf_plan p)
     if (!g_double) {
         if (p->in != p->out) memcpy(p->out, p->in, sizeof(cpx) * (size_t)total);
         for (int a = p->rank - 1; a >= 0; a--)
-            transform_axis_f(p->out, p->n, p->rank, a, p->tw[a]);
+            transform_axis_f(p->out, p->n, p->rank, a, p->tw[a], p->sign);
         return;
     }
-    cpxd *w = (cpxd *)malloc(sizeof(cpxd) * (size_t)total);
-    for (long i = 0; i < total; i++) { w[i].re = p->in[i].re; w[i].im = p->in[i].im; }
+    /* double work array: kept between calls (a 512^3 transform would otherwise map and fault 2 GiB every time) */
+    if (g_work_len < (size_t)total) {
+        free(g_work);
+        g_work = (cpxd *)malloc(sizeof(cpxd) * (size_t)total);
+        g_work_len = g_work ? (size_t)total : 0;
+    }
+    cpxd *w = g_work;
+    const cpx *in = p->in;
+    cpx *out = p->out;
+    int nth = g_threads > 0 ? g_threads : 1;
+    (void)nth;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nth)
+#endif
+    for (long i = 0; i < total; i++) { w[i].re = in[i].re; w[i].im = in[i].im; }
     for (int a = p->rank - 1; a >= 0; a--)
-        transform_axis_d(w, p->n, p->rank, a, p->twd[a]);
-    for (long i = 0; i < total; i++) { p->out[i].re = (float)w[i].re; p->out[i].im = (float)w[i].im; }
-    free(w);
+        transform_axis_d(w, p->n, p->rank, a, p->twd[a], p->sign);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nth)
+#endif
+    for (long i = 0; i < total; i++) { out[i].re = (float)w[i].re; out[i].im = (float)w[i].im; }
 }

@@ -127,22 +127,130 @@ def test_fft_core_on_the_cpu(built, tmp_path):
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
-def test_output_file_format(built, tmp_path):
-    """data/<name>.csv.<step> layout (src/field.cpp:350-402), produced by the product's writer from a host mirror."""
-    code = ("import sys, os; sys.path.insert(0, %r); os.chdir(%r)\n"
+def test_noise_generator_on_the_cpu(built, tmp_path):
+    """cupss_b200/csrc/kstage.cuh is __host__ __device__: philox4x32_10 against the Random123 known-answer vectors, the
+    Hermitian structure of white_noise_mode in the self-conjugate planes kx = 0 / sx/2 (mode == conj(mirror), real
+    self-conjugate bins, E|xi|^2 = N in every class of bins) and the Box-Muller moments, all on the CPU."""
+    exe = tmp_path / "noise_check"
+    src = os.path.join(ROOT, "tests", "host", "noise_check.cu")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-x", "cu", src, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+    assert "6627e8d5 e169c58d bc57ac4c 9b00dbd8" in r.stdout   # Random123 kat_vectors: philox4x32 10, zero counter and key
+
+
+def test_philox_known_answer_vectors_are_the_published_algorithm():
+    """The three known-answer vectors used by tests/host/noise_check.cu, reproduced by an independent pure-Python
+    Philox4x32-10 written from the published round function (Salmon et al., SC'11): multipliers 0xD2511F53 / 0xCD9E8D57,
+    Weyl key increments 0x9E3779B9 / 0xBB67AE85."""
+    def philox(c, k):
+        c, k = list(c), list(k)
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+            k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+        return c
+    assert philox((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox((0xffffffff,) * 4, (0xffffffff,) * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_bench_parity_initial_condition_is_the_test_suites(built):
+    """bench.py builds the 512^3 parity initial condition by broadcasting; it must be bit-identical to cases.smooth_ic."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for shape in [(32, 16, 8), (64, 32, 1), (16, 1, 1), (40, 24, 12)]:
+        assert np.array_equal(cases.smooth_ic(*shape, 0.5, 0.05), bench.smooth_ic(*shape, 0.5, 0.05))
+
+
+SYSTEM_FILE = """# a system file in the reference's format (src/parser.cpp:11-96)
+Fields
+phi 1 1
+iqxphi 0 0
+
+mu 0 1
+Parameters
+a -1.0
+b 1
+k 4.0
+# comment between entries
+Equations
+dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 - 0.5*iqx*iqxphi*phi
+iqxphi = iqx*phi
+mu = a*phi + b*phi^3 + k*q^2*phi
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(ORACLE_F), reason="oracle not built")
+def test_create_from_file_matches_the_reference(built, tmp_path):
+    """evolver::createFromFile (src/parser.cpp:11-96): the same Fields / Parameters / Equations file through the product's
+    text front end and the reference's gives the same plan (fields, output flags via the dump of terms, parameters) and the
+    same printInformation() text; the echo of the file on stdout is the same, too."""
+    path = tmp_path / "system.in"
+    path.write_text(SYSTEM_FILE)
+    code = ("import sys; sys.path.insert(0, %r)\n"
             "from cupss_b200.capi import Evolver\n"
-            "import numpy as np\n"
-            "ev = Evolver(1, 4, 2, 1, 1.0, 1.0, 1.0, 0.1)\n"
-            "ev.createField('phi', True)\n"
-            "ev.setReal('phi', np.arange(8).reshape(1,2,4) * 0.5)\n"
-            "os.makedirs('data', exist_ok=True)\n"
-            "import ctypes\n"
-            "ev.setOutputField('phi', True)\n") % (ROOT, str(tmp_path))
-    # the writer needs the engine for the device->host refresh, so only the pure formatting helper is checked on CPU:
-    # format strings are asserted against the reference's by reading the source of truth in the facade dump
-    src = open(os.path.join(ROOT, "cupss_b200", "host", "field.cpp")).read()
-    assert '"x, y, z, %s\\n"' in src and '"%i, "' in src and '"%." + std::to_string(precision) + "f\\n"' in src
-    subprocess.run([sys.executable, "-c", code], check=True)
+            "lib = sys.argv[1] if sys.argv[1] != 'product' else None\n"
+            "ev = Evolver(0, 16, 16, 1, 1.0, 1.0, 1.0, 0.1, lib=lib)\n"
+            "rc = ev.createFromFile(sys.argv[2])\n"
+            "sys.stdout.flush()\n"
+            "print('RC', rc); print('PLAN'); print(ev.dumpPlan()); print('PARAMS', ev.getParameter('a'), ev.getParameter('b'), ev.getParameter('k'))\n"
+            "sys.stdout.flush()\n"
+            "print('INFO'); sys.stdout.flush(); ev.printInformation()\n") % ROOT
+    outs = {}
+    for tag, lib in (("product", "product"), ("reference", ORACLE_F)):
+        r = subprocess.run([sys.executable, "-c", code, lib, str(path)], capture_output=True, text=True, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = r.stdout
+    assert "RC 0" in outs["product"] and "term" in outs["product"] and "( phi phi phi )" in outs["product"]
+    assert outs["product"] == outs["reference"]
+
+
+def test_print_information_known_answer(built, tmp_path):
+    """the reference's printInformation() text for the Model H system (parser known answer)."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import cases\n"
+            "from cupss_b200.capi import Evolver\n"
+            "ev = Evolver(0, 16, 16, 1, 1.0, 1.0, 1.0, 0.1)\n"
+            "for n, d in cases.MODELH_FIELDS: ev.createField(n, d)\n"
+            "for k, v in cases.MODELH_PARAMS.items(): ev.addParameter(k, v)\n"
+            "for e in cases.MODELH_EQS: ev.addEquation(e)\n"
+            "ev.printInformation()\n") % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = r.stdout
+    assert "Field 0: phi is dynamic. and has 3 explicit terms and 2 implicit terms." in out
+    assert "(d/dt)phi = [+1.000000(q)^(2)-4.000000(q)^(4)]phi [ + (-1.000000)(q)^(2)] ( phi phi phi ) + [ + (-1.000000)] ( iqxphi vx ) + [ + (-1.000000)] ( iqyphi vy )" in out
+    assert "sigxx =  [ + (-2.000000)] ( iqxphi iqxphi ) + [ + (2.000000)] ( iqyphi iqyphi )" in out
+    assert "vx[0.000000+1.000000(q)^(2)] =  [ + (-1.000000)(iqx)^(1)] ( P ) + [ + (1.000000)(iqx)^(1)] ( sigxx ) + [ + (1.000000)(iqy)^(1)] ( sigxy )" in out
+    assert "P[-1.000000(q)^(2)] =  [ + (2.000000)(iqx)^(1)(iqy)^(1)] ( sigxy ) + [ + (1.000000)(iqx)^(2) +  + (-1.000000)(iqy)^(2)] ( sigxx )" in out
+
+
+def test_non_power_of_two_grid_aborts_with_a_message(built, tmp_path):
+    """the engine plans powers of two up to 8192 per axis; anything else is refused by cupss_b200_create
+    with a message (and the C++ layer exits with it) instead of computing something else."""
+    import ctypes as C
+    from cupss_b200 import capi
+    eng = capi.load_engine()
+    h = C.c_void_p()
+    for shape in [(48, 16, 1), (16, 100, 1), (16, 16, 12), (16384, 1, 1)]:
+        rc = eng.cupss_b200_create(C.byref(h), *shape, 1.0, 1.0, 1.0, 0.1)
+        assert rc != 0, shape
+        assert b"power of two" in eng.cupss_b200_last_error(), eng.cupss_b200_last_error()
+
+
+@pytest.mark.skipif(not os.path.exists(cases.ORACLE_U), reason="oracle not built")
+def test_bench_reference_arm_runs_the_named_grid(built):
+    """`bench.py --impl reference` times the reference CPU path on the grid it is asked for (no sampling, no scaling)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "32", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1
+    assert "32^3" in line["config"]["workload"] and "scaled" not in line["cpu_baseline"]["sample"]
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["one_core"]["cores"] == 1
+    assert abs(line["value"] * line["ms_per_step"] / 1e3 - 1) < 1e-9
 
 
 def _slab_worker(rank, world, port, q):

@@ -119,28 +119,44 @@ static void put_pres(std::ostringstream &os, const pres &p)
  * examples/07 and 08 of the reference, written from its description): the field on the quadrant i <= sx/2, j <= sy/2 is
  * reflected into the other three with sign `parity` per reflection.  They are installed through the public members
  * field::hasCB / field::callback exactly like a user's main() would (examples/08_neumann_dirichlet_bc). */
-static void mirror_apply(float2 *a, int sx, int sy, float parity)
+static void mirror_apply(float2 *a, int sx, int sy, int sz, float parity)
 {
-    for (int j = 0; j < sy; ++j)
-        for (int i = 0; i < sx; ++i) {
-            const bool ri = i > sx / 2, rj = j > sy / 2;
-            if (!ri && !rj) continue;
-            const int si = ri ? sx - i : i, sj = rj ? sy - j : j;
-            float sign = 1.0f;
-            if (ri) sign *= parity;
-            if (rj) sign *= parity;
-            a[j * sx + i].x = sign * a[sj * sx + si].x;
-        }
+    /* every z plane on its own: the x/y mirror is local to a plane, so the same function serves 2-D grids (sz = 1), 3-D
+     * grids and the z-slab a rank of a partitioned run is handed (sz = local planes) */
+    for (int k = 0; k < sz; ++k) {
+        float2 *p = a + (size_t)k * sx * sy;
+        for (int j = 0; j < sy; ++j)
+            for (int i = 0; i < sx; ++i) {
+                const bool ri = i > sx / 2, rj = j > sy / 2;
+                if (!ri && !rj) continue;
+                const int si = ri ? sx - i : i, sj = rj ? sy - j : j;
+                float sign = 1.0f;
+                if (ri) sign *= parity;
+                if (rj) sign *= parity;
+                p[j * sx + i].x = sign * p[sj * sx + si].x;
+            }
+    }
 }
-static void mirror_even_cb(evolver *, float2 *a, int sx, int sy, int) { mirror_apply(a, sx, sy, 1.0f); }
-static void mirror_odd_cb(evolver *, float2 *a, int sx, int sy, int) { mirror_apply(a, sx, sy, -1.0f); }
+static void mirror_even_cb(evolver *, float2 *a, int sx, int sy, int sz) { mirror_apply(a, sx, sy, sz, 1.0f); }
+static void mirror_odd_cb(evolver *, float2 *a, int sx, int sy, int sz) { mirror_apply(a, sx, sy, sz, -1.0f); }
+/* kind 2: a NON-symmetric, nonlinear callback -- the strip i < sx/8 is clamped to [-0.05, 0.05] and the strip
+ * sx/2 <= i < sx/2 + sx/16 is scaled by 0.9.  What it leaves is not band-limited in x, which is what tells a product that
+ * reads the dealiased copy unchanged (the reference) from one that low-passes it again. */
+static void clamp_strip_cb(evolver *, float2 *a, int sx, int sy, int sz)
+{
+    for (size_t r = 0; r < (size_t)sy * sz; ++r) {
+        float2 *row = a + r * sx;
+        for (int i = 0; i < sx / 8; ++i) row[i].x = row[i].x > 0.05f ? 0.05f : (row[i].x < -0.05f ? -0.05f : row[i].x);
+        for (int i = sx / 2; i < sx / 2 + sx / 16; ++i) row[i].x *= 0.9f;
+    }
+}
 
 int cupss_capi_set_mirror_callback(void *ev, const char *name, int odd)
 {
     if (EV(ev)->fieldsMap.find(name) == EV(ev)->fieldsMap.end()) return 1;
     field *f = EV(ev)->fieldsMap[name];
     f->hasCB = true;
-    f->callback = odd ? mirror_odd_cb : mirror_even_cb;
+    f->callback = odd == 2 ? clamp_strip_cb : (odd ? mirror_odd_cb : mirror_even_cb);
     return 0;
 }
 
@@ -229,9 +245,16 @@ int cupss_capi_dump_plan(void *ev, char *buf, int buflen)
     return (int)s.size();
 }
 
+void cupss_capi_print_information(void *ev) { EV(ev)->printInformation(); }
+void cupss_capi_copy_host_to_device(void *ev, const char *name)
+{
+    if (EV(ev)->fieldsMap.find(name) != EV(ev)->fieldsMap.end()) EV(ev)->fieldsMap[name]->copyHostToDevice();
+}
+
 #ifdef CUPSS_B200_PRODUCT
 void *cupss_capi_engine_plan(void *ev) { return EV(ev)->enginePlan(); }
 void cupss_capi_set_noise_seed(void *ev, unsigned long long seed) { EV(ev)->setNoiseSeed(seed); }
+unsigned long long cupss_capi_get_noise_seed(void *ev) { return EV(ev)->getNoiseSeed(); }
 void cupss_capi_set_partition(void *ev, int rank, int nranks, const void *id) { EV(ev)->setPartition(rank, nranks, id); }
 #endif
 

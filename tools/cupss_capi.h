@@ -43,17 +43,21 @@ void cupss_capi_initialize_droplet(void *ev, const char *name, float v_out, floa
 void cupss_capi_add_droplet(void *ev, const char *name, float value, float radius, float width, int cx, int cy, int cz);
 void cupss_capi_initialize_half_system(void *ev, const char *name, float v1, float v2, float width, int direction);
 void cupss_capi_initialize_from_file(void *ev, const char *name, const char *path, int skiprows, char delimiter);
-/* installs a built-in host callback (mirror boundary condition, even or odd) on a field: for RUN_CPU evolvers */
+/* installs a built-in host callback on a field (for RUN_CPU evolvers): odd = 0 / 1 mirror boundary condition, even / odd;
+ * odd = 2 a non-symmetric clamp of two boundary strips */
 int cupss_capi_set_mirror_callback(void *ev, const char *name, int odd);
 /* installs a built-in Fourier-space callback (kinds: see cupss_capi.cpp); device_flavour = 1 needs the product and RUN_GPU */
 int cupss_capi_set_fourier_callback(void *ev, const char *name, int kind, int device_flavour);
 /* textual dump of the parsed system from public members (fields, implicit pres, terms, products, noise, aliasing) */
 int cupss_capi_dump_plan(void *ev, char *buf, int buflen);
+void cupss_capi_print_information(void *ev);                  /* evolver::printInformation (stdout) */
+void cupss_capi_copy_host_to_device(void *ev, const char *name);   /* field::copyHostToDevice */
 
 
 /* ---- product build only (-DCUPSS_B200_PRODUCT): access to the engine behind the evolver ---- */
 void *cupss_capi_engine_plan(void *ev);                       /* cupss_b200_plan* (include/cupss_b200.h) */
 void cupss_capi_set_noise_seed(void *ev, unsigned long long seed);
+unsigned long long cupss_capi_get_noise_seed(void *ev);
 void cupss_capi_set_partition(void *ev, int rank, int nranks, const void *nccl_id128);
 
 #ifdef __cplusplus
