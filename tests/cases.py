@@ -12,16 +12,18 @@ REF_GPU = os.path.join(ROOT, "oracle", "_ref", "libcupss_ref_gpu.so")   # the re
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def smooth_ic(sx, sy, sz, amp=0.5, noise=0.05, seed=1):
+def smooth_ic(sx, sy, sz, amp=0.5, noise=0.05, seed=1, kmult=1):
     """O(amp) smooth structure + white noise: exercises the nonlinear terms without sitting on the float32 floor
-    (SURVEY.md Appendix C)."""
+    (SURVEY.md Appendix C).  kmult scales the wavenumbers of the structure: on a large grid the gradients of a 2-period
+    pattern are tiny and DERIVED fields (iqx*phi, stresses, velocities of Model H) would be compared at their own
+    float32 round-off floor instead of at their natural scale."""
     rng = np.random.default_rng(seed)
     z, y, x = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
-    f = amp * np.sin(2 * np.pi * 2 * x / sx)
+    f = amp * np.sin(2 * np.pi * (2 * kmult) * x / sx)
     if sy > 1:
-        f = f * np.cos(2 * np.pi * 3 * y / sy)
+        f = f * np.cos(2 * np.pi * (3 * kmult) * y / sy)
     if sz > 1:
-        f = f * np.cos(2 * np.pi * z / sz)
+        f = f * np.cos(2 * np.pi * kmult * z / sz)
     return (f + noise * (2 * rng.random((sz, sy, sx)) - 1)).astype(np.float32)
 
 
@@ -127,7 +129,7 @@ CASES = {
     "ch2d_64x4096": dict(shape=(64, 4096, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
                          ic=dict(phi=("smooth", (0.4, 0.04))), steps=100, threads=0),
     "modelh_256": dict(shape=(256, 256, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
-                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100, threads=0),
+                       ic=dict(phi=("smooth", (0.5, 0.025, 1, 4))), steps=100, threads=0),   # 8 x 12 periods: linearly unstable band, gradients O(0.1)
     # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
     "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),
