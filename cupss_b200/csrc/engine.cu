@@ -276,6 +276,16 @@ struct Launch {
     double commBytes = 0;   // bytes this rank sends to other GPUs inside this launch (pushed exchange)
     XBarrier xb{};
     void* jitFn = nullptr;   // plan-specialised k stage compiled at run time (AXIS_KSTAGE), else the library's kernels
+    // Lanes: a launch goes to stream `lane` (0 = the plan's main stream).  `waitEv` / `recEv` index the plan's event pool:
+    // the launch waits for waitEv before it starts and records recEv when it is queued (cross-lane dependencies of the
+    // chunked pipelines).  `joinBefore`: every lane used so far is joined into the main stream first.  The list order is
+    // always a valid serial order, so running a list on one stream (profile_step) is correct too.
+    int lane = 0, waitEv = -1, recEv = -1;
+    bool joinBefore = false;
+    int pipe = -1;           // launches of one multi-lane pipeline share an id >= 0; the launch after a pipeline joins the lanes
+    int group = -1;          // launches of one pipeline (same id >= 0) are timed as one unit by profile_step
+    char groupName[64] = "";
+    double groupBytes = 0;   // DRAM-level bytes of the whole pipeline (set on its first launch)
 };
 
 int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
@@ -307,6 +317,15 @@ struct cupss_b200_plan {
     bool prune = true;     // skip the parts of inverse transforms that the dealias mask makes identically zero
     void* comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // extra streams / events of the chunked pipelines (lane 0 is `stream`); lane 1 has the higher priority: it carries the
+    // downstream kernel of a producer -> consumer pair, whose CTAs should get the SM slots the producer's CTAs free
+    static constexpr int kMaxLanes = 3;
+    cudaStream_t laneStream[kMaxLanes] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> evPool;
+    cudaEvent_t forkEv[kMaxLanes] = {nullptr, nullptr, nullptr}, joinEv[kMaxLanes] = {nullptr, nullptr, nullptr};
+    int nextEv = 0, nextGroup = 0, nextPipe = 0;
+    int zChunk = 0;        // planes per chunk of the x -> forward-y pipeline (0: off)
+    int xChunks = 1;       // column chunks of the slab-exchange pipeline (1: off, launches run one after the other)
     // Peer-memory exchange arena (multi-GPU): [header: flags, epochs, error][slot 0][slot 1]...; every rank maps
     // every peer's arena through CUDA IPC, and the y / z pass kernels store their output rows straight into the
     // owner's slot over NVLink (no NCCL, no staging copy on the hot path).
@@ -366,6 +385,7 @@ struct cupss_b200_plan {
     void fill_common(AxisArgs& a, int L) {
         a.ncol = ncol;
         a.ncolTiles = (ncol + axis_tile_cols(L) - 1) / axis_tile_cols(L);
+        a.ctBase = 0;
         a.sx = sx; a.sy = sy; a.sz = sz;
         a.maskOn = 0; a.cutx = a.cuty = a.cutz = 0;
         a.pruneOn = 0; a.pruneCutX = a.pruneCutY = 0; a.rowCut = -1;
@@ -465,7 +485,40 @@ struct cupss_b200_plan {
         out.push_back(l);
     }
 
-    int run_launch(Launch& l) {
+    int lane_stream(int lane, cudaStream_t* out) {
+        if (lane <= 0) { *out = stream; return CUPSS_B200_OK; }
+        if (lane >= kMaxLanes) return fail(CUPSS_B200_ERR_STATE, "internal: lane %d", lane);
+        if (!laneStream[lane]) {
+            int lo = 0, hi = 0;   // lo: least priority (numerically largest), hi: greatest
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&laneStream[lane], cudaStreamNonBlocking, lane == 1 ? hi : lo));
+            CK(cudaEventCreateWithFlags(&forkEv[lane], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&joinEv[lane], cudaEventDisableTiming));
+        }
+        *out = laneStream[lane];
+        return CUPSS_B200_OK;
+    }
+    int pool_event(int idx, cudaEvent_t* out) {
+        while ((int)evPool.size() <= idx) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            evPool.push_back(e);
+        }
+        *out = evPool[idx];
+        return CUPSS_B200_OK;
+    }
+    int join_lanes(bool (&forked)[kMaxLanes]) {
+        for (int ln = 1; ln < kMaxLanes; ++ln)
+            if (forked[ln]) {
+                CK(cudaEventRecord(joinEv[ln], laneStream[ln]));
+                CK(cudaStreamWaitEvent(stream, joinEv[ln], 0));
+                forked[ln] = false;
+            }
+        return CUPSS_B200_OK;
+    }
+
+    int run_launch(Launch& l) { return run_launch(l, stream); }
+    int run_launch(Launch& l, cudaStream_t stream) {
         switch (l.kind) {
             case Launch::XPASS: CK(launch_xpass(sx, l.mode, l.xa, stream)); break;
             case Launch::AXIS_PLAIN: CK(launch_axis_plain(l.L, l.dir, l.ax, stream)); break;
@@ -496,10 +549,35 @@ struct cupss_b200_plan {
         }
         return CUPSS_B200_OK;
     }
-    int run_list(std::vector<Launch>& v) {
-        for (auto& l : v) CKR(run_launch(l));
-        return CUPSS_B200_OK;
+    // Launches [b, e) of a list, each on its lane; every lane that was used is joined into the main stream at the end, so the
+    // caller (and a stream capture) only ever sees the main stream.
+    int run_range(std::vector<Launch>& v, size_t b, size_t e) {
+        bool forked[kMaxLanes] = {false, false, false};
+        for (size_t i = b; i < e; ++i) {
+            Launch& l = v[i];
+            if (l.joinBefore) CKR(join_lanes(forked));
+            cudaStream_t st;
+            CKR(lane_stream(l.lane, &st));
+            if (l.lane > 0 && !forked[l.lane]) {   // the lane starts after everything queued on the main stream so far
+                CK(cudaEventRecord(forkEv[l.lane], stream));
+                CK(cudaStreamWaitEvent(st, forkEv[l.lane], 0));
+                forked[l.lane] = true;
+            }
+            if (l.waitEv >= 0) {
+                cudaEvent_t ev;
+                CKR(pool_event(l.waitEv, &ev));
+                CK(cudaStreamWaitEvent(st, ev, 0));
+            }
+            CKR(run_launch(l, st));
+            if (l.recEv >= 0) {
+                cudaEvent_t ev;
+                CKR(pool_event(l.recEv, &ev));
+                CK(cudaEventRecord(ev, st));
+            }
+        }
+        return join_lanes(forked);
     }
+    int run_list(std::vector<Launch>& v) { return run_range(v, 0, v.size()); }
 
     // ------------------------------------------------------------ full transforms (upload / download; not on the hot path)
     // real [zl][sy][sx] (realBuf) -> spectrum S
@@ -680,6 +758,102 @@ struct cupss_b200_plan {
         return run_list(v);
     }
 
+    // z-chunked software pipeline of the x passes (main stream) and the forward y passes (lane 1, higher priority): the y pass
+    // of chunk c runs next to the x pass of chunk c+1.  The x pass is bound by issue slots and the y pass by memory, so the two
+    // fill each other's idle resource, and a chunk of the x-pass output (zChunk planes x 1.1 MB) is still in the 126 MB L2 when
+    // the y pass reads it: that read (4 B per point) never reaches HBM.
+    void emit_xy_pipeline(std::vector<Launch>& out, const std::vector<Launch>& xs, const std::vector<Launch>& ys, const char* tag) {
+        const int nchunk = zl / zChunk, gid = nextGroup++, pid = nextPipe++;
+        const double frac = 1.0 / nchunk;
+        double gbytes = 0;
+        for (const Launch& x : xs) gbytes += x.bytes;
+        for (const Launch& y : ys) gbytes += y.bytes - spec_bytes();   // the y pass reads what the x pass just left in L2
+        bool first = true;
+        for (int c = 0; c < nchunk; ++c) {
+            const long long z0 = (long long)c * zChunk;
+            const int ev = nextEv++;
+            for (size_t i = 0; i < xs.size(); ++i) {
+                Launch x = xs[i];
+                for (int q = 0; q < x.xa.nIn; ++q) x.xa.in[q] += z0 * sy * pitch;
+                for (int q = 0; q < x.xa.nOut; ++q) x.xa.out[q] += z0 * sy * pitch;
+                x.xa.nlines = (long long)zChunk * sy;
+                x.bytes *= frac;
+                x.lane = 0;
+                if (i + 1 == xs.size()) x.recEv = ev;
+                x.group = gid; x.pipe = pid;
+                if (first) { snprintf(x.groupName, sizeof x.groupName, "xyfwd_%s", tag); x.groupBytes = gbytes; first = false; }
+                out.push_back(x);
+            }
+            for (size_t i = 0; i < ys.size(); ++i) {
+                Launch y = ys[i];
+                y.ax.in += z0 * y.ax.ain.bs;
+                y.ax.out += z0 * y.ax.aout.bs;
+                y.ax.nbatch = zChunk;
+                y.bytes *= frac;
+                y.lane = 1;
+                if (i == 0) y.waitEv = ev;
+                y.group = gid; y.pipe = pid;
+                out.push_back(y);
+            }
+        }
+    }
+
+    // Column chunk [t0, t0 + nt) of a strided-axis launch.
+    Launch column_chunk(const Launch& l, int t0, int nt) const {
+        Launch c = l;
+        const int C = axis_tile_cols(l.L);
+        const double frac = (double)(std::min(ncol, (t0 + nt) * C) - std::min(ncol, t0 * C)) / ncol;
+        c.ax.ctBase = t0; c.ax.ncolTiles = nt;
+        c.bytes *= frac; c.commBytes *= frac;
+        return c;
+    }
+    static bool chunk_live(const Launch& l, int t0) {   // does an inverse launch produce anything from column tile t0 on?
+        return !l.ax.pruneOn || t0 * axis_tile_cols(l.L) <= l.ax.pruneCutX;
+    }
+    // Slab-partitioned sweep as a column-chunked pipeline.  The kx column tiles are split into xChunks chunks; per chunk c
+    //   lane 0 (main):  forward y pass of every product group, rows pushed into the owners' receive slots      YF(c)
+    //   lane 1:         barrier(c) -> [last-axis forward passes of further groups] -> k stage (pushes its fused
+    //                   inverse z part) -> [masked inverse z passes of further dealiased fields, pushed]            KS(c)
+    //   lane 2:         barrier(c) -> inverse y passes                                                              YI(c)
+    // YF(c+1) -- bound by the NVLink stores -- runs next to KS(c) and YI(c-1), which are bound by local HBM; the barriers wait
+    // on per-chunk flags next to the kernels of the other lanes instead of in front of them.  Hazards: a receive slot chunk is
+    // rewritten in the next step only after the peers have read it -- forward slots: YF(c, n+1) follows this rank's last
+    // barrier of step n on lane 2, which every peer only signals after ALL its k-stage chunks of step n; inverse slots:
+    // KS(c, n+1) follows barrier(c, n+1) of lane 1, which a peer only signals from step n+1, i.e. after its YI(., n).
+    void emit_exchange_pipeline(std::vector<Launch>& out, const std::vector<Launch>& yf, const std::vector<Launch>& lf,
+                                const std::vector<Launch>& kk, const std::vector<Launch>& li, const std::vector<Launch>& yi) {
+        const int nct = kk[0].ax.ncolTiles;
+        const int nch = std::min(xChunks, nct);
+        // tiles per chunk: the remainder goes to the LAST chunks (beyond the dealias cut-off: nothing to send back there)
+        std::vector<int> start(nch + 1, 0);
+        for (int c = 0; c < nch; ++c) start[c + 1] = start[c] + nct / nch + (c >= nch - nct % nch ? 1 : 0);
+        const size_t first = out.size();
+        const int pid = nextPipe++;
+        for (int c = 0; c < nch; ++c) {
+            const int t0 = start[c], nt = start[c + 1] - start[c];
+            const int evF = nextEv++, evK = nextEv++;
+            for (size_t i = 0; i < yf.size(); ++i) {
+                Launch l = column_chunk(yf[i], t0, nt);
+                l.lane = 0;
+                if (i + 1 == yf.size()) l.recEv = evF;
+                out.push_back(l);
+            }
+            add_barrier(out, "xbar_fwd");
+            out.back().lane = 1; out.back().waitEv = evF;
+            for (const Launch& z : lf) { Launch l = column_chunk(z, t0, nt); l.lane = 1; out.push_back(l); }
+            { Launch l = column_chunk(kk[0], t0, nt); l.lane = 1; out.push_back(l); }
+            for (const Launch& z : li) if (chunk_live(z, t0)) { Launch l = column_chunk(z, t0, nt); l.lane = 1; out.push_back(l); }
+            out.back().recEv = evK;
+            bool anyInv = false;
+            for (const Launch& y : yi) anyInv = anyInv || chunk_live(y, t0);
+            if (!anyInv && c + 1 < nch) continue;
+            add_barrier(out, "xbar_inv");
+            out.back().lane = 2; out.back().waitEv = evK;
+            for (const Launch& y : yi) if (chunk_live(y, t0)) { Launch l = column_chunk(y, t0, nt); l.lane = 2; out.push_back(l); }
+        }
+        for (size_t i = first; i < out.size(); ++i) out[i].pipe = pid;
+    }
+
     int build_stage(bool dyn, std::vector<Launch>& out) {
         std::vector<int> outs;
         for (size_t f = 0; f < fields.size(); ++f) if (fields[f].dynamic == dyn) outs.push_back((int)f);
@@ -709,6 +883,7 @@ struct cupss_b200_plan {
         std::vector<const float2*> groupSpec(groups.size(), nullptr);   // input of the last-axis forward pass per group
 
         // ---- x passes (greedy split under the kernel's descriptor limits)
+        std::vector<Launch> xs;
         size_t g0 = 0;
         while (g0 < groups.size()) {
             Launch x{};
@@ -774,9 +949,18 @@ struct cupss_b200_plan {
             CKR(get_twiddle(sx, &x.xa.tw));
             CKR(get_twiddle_x3(&x.xa.tw3));
             x.bytes = (inFrac + x.xa.nOut) * spec_bytes();
-            out.push_back(x);
+            xs.push_back(x);
             g0 = g1;
         }
+        // Single GPU, 3-D: the x passes and the forward y passes both work plane by plane, so they run as a z-chunked software
+        // pipeline on two streams (emit_xy_pipeline); otherwise the x passes go out whole, right here.
+        const bool xyPipe = dim == 3 && nranks == 1 && zChunk > 0 && zl >= 2 * zChunk && zl % zChunk == 0 && !groups.empty();
+        if (!xyPipe) for (Launch& x : xs) out.push_back(x);
+        std::vector<Launch> ys;
+        // Slab-partitioned run with the fused push exchange: the exchange side of the sweep is collected per kind and emitted as
+        // a column-chunked pipeline over three lanes (emit_exchange_pipeline) instead of one launch after the other.
+        const bool xPipe = dim == 3 && nranks > 1 && useP2P && xChunks > 1 && !groups.empty();
+        std::vector<Launch> pipeYF, pipeLF, pipeK, pipeLI, pipeYI;
 
         // ---- forward y passes (3-D) and slab exchange
         if (dim == 3) {
@@ -795,12 +979,12 @@ struct cupss_b200_plan {
                     set_push(y.ax, slot, true);
                     y.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
                     snprintf(y.name, sizeof y.name, "yfwd_push_%s", tag);
-                    out.push_back(y);
-                    add_barrier(out, "xbar_fwd");
+                    if (xPipe) pipeYF.push_back(y);
+                    else { out.push_back(y); add_barrier(out, "xbar_fwd"); }
                     groupSpec[g] = arena_slot_ptr(rank, slot);
                     continue;
                 }
-                out.push_back(y);
+                if (xyPipe) ys.push_back(y); else out.push_back(y);
                 groupSpec[g] = w4;
                 if (nranks > 1) {
                     float2* r;
@@ -810,10 +994,12 @@ struct cupss_b200_plan {
                 }
             }
         }
+        if (xyPipe) emit_xy_pipeline(out, xs, ys, tag);
 
         // ---- k stage
         Launch k{};
         k.kind = Launch::AXIS_KSTAGE;
+        k.joinBefore = xyPipe;
         snprintf(k.name, sizeof k.name, "kstage_%s", tag);
         CKR(make_last_axis(k.ax, &k.L));
         KStageD& ks = k.ks;
@@ -850,7 +1036,7 @@ struct cupss_b200_plan {
             CKR(get_scratch(sc++, &that));
             z.ax.in = groupSpec[g]; z.ax.out = that;
             z.bytes = 2.0 * spec_bytes();
-            out.push_back(z);
+            if (xPipe) pipeLF.push_back(z); else out.push_back(z);
             if (ks.nsrc >= KS_MAX_SRC) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
             ks.src[ks.nsrc] = that;
             srcOfGroup[g] = ks.nsrc++;
@@ -971,12 +1157,12 @@ struct cupss_b200_plan {
             set_push(k.ax, slot, false);
             k.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
             snprintf(k.name, sizeof k.name, "kstage_push_%s", tag);
-            out.push_back(k);
-            add_barrier(out, "xbar_inv");
+            if (xPipe) pipeK.push_back(k);
+            else { out.push_back(k); add_barrier(out, "xbar_inv"); }
             w1s.push_back({invField, arena_slot_ptr(rank, slot)});
             pushed.push_back(1);
         } else {
-            out.push_back(k);
+            if (xPipe) pipeK.push_back(k); else out.push_back(k);
             if (invField >= 0 && dim == 3) { w1s.push_back({invField, invOut}); pushed.push_back(0); }
         }
 
@@ -992,8 +1178,8 @@ struct cupss_b200_plan {
                 set_push(z.ax, slot, false);
                 z.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
                 snprintf(z.name, sizeof z.name, "lastinv_push_%s", tag);
-                out.push_back(z);
-                add_barrier(out, "xbar_inv");
+                if (xPipe) pipeLI.push_back(z);
+                else { out.push_back(z); add_barrier(out, "xbar_inv"); }
                 w1s.push_back({f, arena_slot_ptr(rank, slot)});
                 pushed.push_back(1);
                 continue;
@@ -1012,8 +1198,9 @@ struct cupss_b200_plan {
             }
             Launch y;
             CKR(yinv_launch(pr.first, tag, yin, y));
-            out.push_back(y);
+            if (xPipe) pipeYI.push_back(y); else out.push_back(y);
         }
+        if (xPipe) emit_exchange_pipeline(out, pipeYF, pipeLF, pipeK, pipeLI, pipeYI);
         return CUPSS_B200_OK;
     }
 
@@ -1061,10 +1248,12 @@ struct cupss_b200_plan {
             CKR(ensure_arena((size_t)arenaNext));
         }
         step.clear();
-        arenaNext = 0; nextPt = 0;
+        arenaNext = 0; nextPt = 0; nextEv = 0; nextGroup = 0; nextPipe = 0;
         CKR(build_stage(false, step));
         stageSplit = step.size();
         CKR(build_stage(true, step));
+        for (size_t i = 1; i < step.size(); ++i)   // the launch that follows a multi-lane pipeline waits for all of its lanes
+            if (step[i - 1].pipe >= 0 && step[i].pipe != step[i - 1].pipe) step[i].joinBefore = true;
         if (nextPt > XH_EPOCH / CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "too many exchange points (%d)", nextPt);
         Launch b{};
         b.kind = Launch::BUMP;
@@ -1091,8 +1280,7 @@ struct cupss_b200_plan {
     int do_stage(int which) {
         if (!finalized) return fail(CUPSS_B200_ERR_STATE, "step before finalize");
         const size_t b = which == 0 ? 0 : stageSplit, e = which == 0 ? stageSplit : step.size();
-        for (size_t i = b; i < e; ++i) CKR(run_launch(step[i]));
-        return CUPSS_B200_OK;
+        return run_range(step, b, e);
     }
     // Real view of a field for a callback: which = 0 the field itself, 1 its dealiased copy (what products read).
     // Partitioned plans: the view is this rank's z-slab [zl][sy][sx] (collective for which == 0: the full transform exchanges slabs).
@@ -1221,6 +1409,8 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     p->useGraph = !(ng && ng[0] == '1');
     const char* np_ = getenv("CUPSS_B200_NO_PRUNE");
     p->prune = !(np_ && np_[0] == '1');
+    if (const char* zc = getenv("CUPSS_B200_ZCHUNK")) p->zChunk = atoi(zc);
+    if (const char* xc = getenv("CUPSS_B200_XCHUNKS")) p->xChunks = std::max(1, atoi(xc));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));
@@ -1247,6 +1437,12 @@ void cupss_b200_destroy(cupss_b200_plan* p) {
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    for (cudaEvent_t e : p->evPool) cudaEventDestroy(e);
+    for (int ln = 1; ln < cupss_b200_plan::kMaxLanes; ++ln) {
+        if (p->forkEv[ln]) cudaEventDestroy(p->forkEv[ln]);
+        if (p->joinEv[ln]) cudaEventDestroy(p->joinEv[ln]);
+        if (p->laneStream[ln]) cudaStreamDestroy(p->laneStream[ln]);
+    }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -1513,22 +1709,31 @@ int cupss_b200_time_steps(cupss_b200_plan* p, int nsteps, float* ms) {
 
 int cupss_b200_profile_step(cupss_b200_plan* p, int nmax, char* names, float* ms, double* bytes, int* n) {
     if (!p || !p->finalized) return fail(CUPSS_B200_ERR_STATE, "profile before finalize");
-    const int cnt = (int)p->step.size();
+    // units: single launches, or whole pipelines (consecutive launches of one group, run on their lanes and timed fork to join)
+    std::vector<std::pair<size_t, size_t>> units;
+    for (size_t i = 0; i < p->step.size();) {
+        size_t j = i + 1;
+        if (p->step[i].group >= 0) while (j < p->step.size() && p->step[j].group == p->step[i].group) ++j;
+        units.push_back({i, j});
+        i = j;
+    }
+    const int cnt = (int)units.size();
     std::vector<cudaEvent_t> ev(cnt + 1);
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaEventRecord(ev[0], p->stream));
     for (int i = 0; i < cnt; ++i) {
-        CKR(p->run_launch(p->step[i]));
+        CKR(p->run_range(p->step, units[i].first, units[i].second));
         CK(cudaEventRecord(ev[i + 1], p->stream));
     }
     CK(cudaStreamSynchronize(p->stream));
     for (int i = 0; i < cnt && i < nmax; ++i) {
         float t = 0;
         CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        const Launch& l0 = p->step[units[i].first];
         if (ms) ms[i] = t;
-        if (bytes) bytes[i] = p->step[i].bytes;
-        if (names) snprintf(names + 64 * i, 64, "%s", p->step[i].name);
+        if (bytes) bytes[i] = l0.group >= 0 ? l0.groupBytes : l0.bytes;
+        if (names) snprintf(names + 64 * i, 64, "%s", l0.group >= 0 ? l0.groupName : l0.name);
     }
     for (auto& e : ev) cudaEventDestroy(e);
     if (n) *n = cnt < nmax ? cnt : nmax;
@@ -1543,7 +1748,7 @@ int cupss_b200_launches_per_step(cupss_b200_plan* p) {
 }
 double cupss_b200_bytes_per_step(cupss_b200_plan* p) {
     double b = 0;
-    if (p) for (auto& l : p->step) if (l.kind != Launch::A2A) b += l.bytes;
+    if (p) for (auto& l : p->step) if (l.kind != Launch::A2A) b += l.group >= 0 ? l.groupBytes : l.bytes;   // groupBytes: first launch of a pipeline only
     return b;
 }
 double cupss_b200_comm_bytes_per_step(cupss_b200_plan* p) {

@@ -23,7 +23,8 @@ struct AxisArgs {
     float2* out;
     AxisAddr ain, aout;
     int ncol;        // valid columns (sx/2 + 1)
-    int ncolTiles;   // ceil(ncol / C)
+    int ncolTiles;   // column tiles of THIS launch (ceil(ncol / C) unless the pass is split into column chunks)
+    int ctBase;      // first column tile of this launch (column-chunked exchange pipeline, engine.cu)
     int nbatch;
     const float2* tw;
     int axis;        // k index carried by the rows: 1 = ky, 2 = kz, 0 = none (L = 1)

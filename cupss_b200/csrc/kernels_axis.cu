@@ -80,10 +80,12 @@ static cudaError_t launch_plain_L(int dir, const AxisArgs& a, cudaStream_t st) {
     // pruned inverse passes: column tiles beyond the dealias cut-off produce nothing -- they are not launched at all
     AxisArgs la = a;
     if (a.pruneOn && dir > 0) {
-        const int live = a.pruneCutX / AxisCfg<L>::C + 1;
+        const int live = a.pruneCutX / AxisCfg<L>::C + 1 - a.ctBase;   // live tiles of this launch's column chunk
+        if (live <= 0) return cudaSuccess;
         if (live < la.ncolTiles) la.ncolTiles = live;
     }
     const unsigned grid = (unsigned)la.ncolTiles * (unsigned)la.nbatch;
+    if (grid == 0) return cudaSuccess;
     if (dir < 0) {
         if (a.maskOn) return cudaErrorInvalidValue;   // the mask only exists on inverse transforms
         axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);

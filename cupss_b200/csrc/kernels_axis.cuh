@@ -50,6 +50,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// Level twiddle table -> shared memory with the same asynchronous copies as the tile (no LDG -> STS round trip through
+// registers in front of the first barrier; profiles/r02z: that chain drew 11-14 % of the stall samples of these kernels).
+template <int L, int THREADS>
+__device__ __forceinline__ void tw_fetch(float2* twS, const float2* __restrict__ tw) {
+    constexpr int LEN = TwTable<L>::LEN;
+    if constexpr (LEN >= 2 && LEN % 2 == 0) {
+        for (int i = threadIdx.x; i < LEN / 2; i += THREADS) cp_async16(reinterpret_cast<float4*>(twS) + i, tw + 2 * i);
+    } else {
+        for (int i = threadIdx.x; i < LEN; i += THREADS) twS[i] = __ldg(tw + i);
+    }
+}
+
 // Tile prologue: position p of the tile <- row rowOf(p) of the input (natural order for a forward transform, frequency
 // order for an inverse one).  Rows that are known zeros (keep(row) false) and invalid column pairs are zero-filled.
 template <int L, int CP, int TV, class RowOf, class Keep>
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     float4* tile = smem4;
     float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
     const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
-    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles, b = blockIdx.x / (unsigned)a.ncolTiles;
+    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = blockIdx.x / (unsigned)a.ncolTiles;
     const unsigned col = ct * C + 2 * cp;
     const bool valid = col < (unsigned)a.ncol;
 
@@ -106,9 +118,7 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
         const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
         if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
     }
-    auto load_twiddles = [&]() {
-        for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
-    };
+    auto load_twiddles = [&]() { tw_fetch<L, Cfg::THREADS>(twS, a.tw); };
 
     const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
     float2* lbase = a.out + (b * (unsigned)a.aout.bs + col);
@@ -184,7 +194,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     float4* tile = smem4;
     float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
     const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
-    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles, b = blockIdx.x / (unsigned)a.ncolTiles;
+    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = blockIdx.x / (unsigned)a.ncolTiles;
     const unsigned col = ct * C + 2 * cp;
     const bool valid = col < (unsigned)a.ncol, valid1 = col + 1 < (unsigned)a.ncol;
 
@@ -206,7 +216,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     if constexpr (n > 1) {
         if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
     }
-    for (int i = threadIdx.x; i < TwTable<L>::LEN; i += Cfg::THREADS) twS[i] = __ldg(a.tw + i);
+    tw_fetch<L, Cfg::THREADS>(twS, a.tw);
     if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
         // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
         const float2* p0 = ks.src[0] + (b * (unsigned)a.aout.bs + ct * C);

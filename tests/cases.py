@@ -129,7 +129,12 @@ CASES = {
     "ch2d_64x4096": dict(shape=(64, 4096, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
                          ic=dict(phi=("smooth", (0.4, 0.04))), steps=100, threads=0),
     "modelh_256": dict(shape=(256, 256, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
-                       ic=dict(phi=("smooth", (0.5, 0.025, 1, 4))), steps=100, threads=0),   # 8 x 12 periods: linearly unstable band, gradients O(0.1)
+                       ic=dict(phi=("smooth", (0.5, 0.025, 1, 4))), steps=100, threads=0,   # 8 x 12 periods: linearly unstable band, gradients O(0.1)
+                       # Derived fields built from differences of nearly equal terms (projected velocity, its curl): a plain float32
+                       # pipeline (numpy restatement, complex64) sits 2.4e-5 / 4.0e-5 / 1.4e-4 from float64 on vx / vy / w and 1e-5 on
+                       # the stresses after 100 steps, and the reference's own float32 run 0.7e-5 / 0.8e-5 / 2.5e-5
+                       # (tests/golden/f32_floor.py).  Tolerances = 1.5 x that floor; the dynamic field and its gradients keep 1e-5.
+                       tol=dict(sigxx=1.5e-5, sigxy=1.5e-5, P=1.5e-5, vx=3.6e-5, vy=6e-5, w=2.1e-4)),
     # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
     "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),
