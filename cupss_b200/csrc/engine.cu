@@ -27,6 +27,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap types only; the encoder is resolved at run time (cudaGetDriverEntryPoint), libcuda is not linked
+
 #include "../../include/cupss_b200.h"
 #include "kernels.h"
 
@@ -240,6 +242,66 @@ static bool jit_compile(const std::string& src, std::vector<char>* cubin, std::s
     return n > 0;
 }
 
+// ---------------------------------------------------------------- TMA descriptors of the strided-axis tile prologues
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static bool tried = false;
+    static TensorMapEncodeTiledFn fn = nullptr;
+    if (!tried) {
+        tried = true;
+        const char* off = getenv("CUPSS_B200_TMA");
+        if (off && off[0] == '0') return nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// Tensor map of the INPUT array of a strided-axis launch (kernels.h: AxisArgs::tmap).  Leaves tmaOn = 0 (per-thread cp.async
+// prologue) when the transform has a single level, the encoder is unavailable or the live row range does not split into boxes.
+static void prepare_tma(cupss::AxisArgs& a, int L, bool kstage) {
+    a.tmaOn = 0;
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || L < 32 || !a.in) return;
+    const int C = cupss::axis_tile_cols(L);
+    const long long rpc = (long long)a.ain.rpcMask + 1, nchunk = L / rpc;
+    int B = L < 256 ? L : 256;
+    if (!kstage && a.rowCut >= 0) {   // pruned inverse: boxes over [0, cut) and [L - cut, L)
+        const int c = a.rowCut;
+        if (c > 0) { B = 256; while (B > 1 && (c % B)) B >>= 1; }
+        if (c > 0 && B < 16) return;
+    }
+    struct Dim { unsigned long long size, stride; unsigned box; int role; };
+    const long long rs = a.ain.rs, cs = a.ain.cs, bs = a.ain.bs;
+    Dim d[3] = {{(unsigned long long)rpc, (unsigned long long)rs * 8ull, (unsigned)(B < rpc ? B : rpc), 0},
+                {(unsigned long long)nchunk, (unsigned long long)cs * 8ull, (unsigned)(B < rpc ? 1 : B / rpc), 1},
+                {(unsigned long long)a.nbatch, (unsigned long long)bs * 8ull, 1u, 2}};
+    unsigned long long top = 0;
+    for (const Dim& x : d) if (x.size > 1) top = std::max(top, x.size * x.stride);
+    if (top == 0) top = 128;
+    for (Dim& x : d) {
+        if (x.size > 1 && (x.stride == 0 || (x.stride & 15ull))) return;
+        if (x.size <= 1) { x.size = 1; x.stride = top; top *= 2; }   // degenerate axes: any legal stride, kept monotonic
+    }
+    std::stable_sort(d, d + 3, [](const Dim& p, const Dim& q) { return p.stride < q.stride; });
+    cuuint64_t gdim[4] = {(cuuint64_t)(2 * a.ncol), d[0].size, d[1].size, d[2].size};
+    cuuint64_t gstr[3] = {d[0].stride, d[1].stride, d[2].stride};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * C), d[0].box, d[1].box, d[2].box};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUtensorMap tm;
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(a.in), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+    static_assert(sizeof(CUtensorMap) == sizeof(a.tmap), "tensor map size");
+    memcpy(a.tmap, &tm, sizeof tm);
+    for (int k = 0; k < 3; ++k) a.tmaSlot[k] = d[k].role;
+    a.tmaBoxRows = B;
+    a.tmaOn = 1;
+}
+
 // ---------------------------------------------------------------- plan data model
 namespace {
 
@@ -283,6 +345,7 @@ struct Launch {
     int lane = 0, waitEv = -1, recEv = -1;
     bool joinBefore = false;
     int pipe = -1;           // launches of one multi-lane pipeline share an id >= 0; the launch after a pipeline joins the lanes
+    bool tmaReady = false;   // AXIS_*: the tensor map of the input was built (lazily, at the first launch)
     int group = -1;          // launches of one pipeline (same id >= 0) are timed as one unit by profile_step
     char groupName[64] = "";
     double groupBytes = 0;   // DRAM-level bytes of the whole pipeline (set on its first launch)
@@ -325,6 +388,7 @@ struct cupss_b200_plan {
     cudaEvent_t forkEv[kMaxLanes] = {nullptr, nullptr, nullptr}, joinEv[kMaxLanes] = {nullptr, nullptr, nullptr};
     int nextEv = 0, nextGroup = 0, nextPipe = 0;
     int zChunk = 0;        // planes per chunk of the x -> forward-y pipeline (0: off)
+    int zChunkLanes = 2;
     int xChunks = 1;       // column chunks of the slab-exchange pipeline (1: off, launches run one after the other)
     // Peer-memory exchange arena (multi-GPU): [header: flags, epochs, error][slot 0][slot 1]...; every rank maps
     // every peer's arena through CUDA IPC, and the y / z pass kernels store their output rows straight into the
@@ -521,8 +585,12 @@ struct cupss_b200_plan {
     int run_launch(Launch& l, cudaStream_t stream) {
         switch (l.kind) {
             case Launch::XPASS: CK(launch_xpass(sx, l.mode, l.xa, stream)); break;
-            case Launch::AXIS_PLAIN: CK(launch_axis_plain(l.L, l.dir, l.ax, stream)); break;
+            case Launch::AXIS_PLAIN:
+                if (!l.tmaReady) { prepare_tma(l.ax, l.L, false); l.tmaReady = true; }
+                CK(launch_axis_plain(l.L, l.dir, l.ax, stream));
+                break;
             case Launch::AXIS_KSTAGE:
+                if (!l.tmaReady) { prepare_tma(l.ax, l.L, true); l.tmaReady = true; }
                 if (l.jitFn) {
                     int threads = 0, minb = 0;
                     size_t smem = 0;
@@ -790,7 +858,7 @@ struct cupss_b200_plan {
                 y.ax.out += z0 * y.ax.aout.bs;
                 y.ax.nbatch = zChunk;
                 y.bytes *= frac;
-                y.lane = 1;
+                y.lane = zChunkLanes > 1 ? 1 : 0;   // one lane: plain alternation x(c), y(c), x(c+1), ... (L2 hand-off only)
                 if (i == 0) y.waitEv = ev;
                 y.group = gid; y.pipe = pid;
                 out.push_back(y);
@@ -1410,6 +1478,7 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     const char* np_ = getenv("CUPSS_B200_NO_PRUNE");
     p->prune = !(np_ && np_[0] == '1');
     if (const char* zc = getenv("CUPSS_B200_ZCHUNK")) p->zChunk = atoi(zc);
+    if (const char* zl = getenv("CUPSS_B200_ZCHUNK_LANES")) p->zChunkLanes = atoi(zl);
     if (const char* xc = getenv("CUPSS_B200_XCHUNKS")) p->xChunks = std::max(1, atoi(xc));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));

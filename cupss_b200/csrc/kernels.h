@@ -43,6 +43,13 @@ struct AxisArgs {
     long long pushRs, pushBs, pushBase;
     float2* push[CUPSS_MAX_PEERS];   // base of every rank's exchange arena (header: flags / epochs / error word)
     int rank, nranks;
+    // TMA tile prologue (cp.async.bulk.tensor, kernels_axis.cuh: tile_fetch_tma).  `tmap` is a CUtensorMap of the input array
+    // seen as float32 [2*ncol][.][.][.] -- columns, then (row inside a chunk, chunk, batch) sorted by stride; tmaSlot[k] says
+    // which of those three the k-th outer coordinate is.  One instruction moves a box of tmaBoxRows rows x 128 bytes straight
+    // into the tile; columns beyond ncol are zero-filled by the hardware.  tmaOn = 0: per-thread cp.async path.
+    int tmaOn, tmaBoxRows;
+    int tmaSlot[3];
+    alignas(64) unsigned long long tmap[16];
 };
 // Arena header layout (32-bit words from the arena base): flag table [pt][CUPSS_MAX_PEERS], epochs, error word.
 constexpr int XH_FLAGS = 0, XH_EPOCH = 1024, XH_ERROR = 2048;

@@ -10,7 +10,8 @@ template <int L> struct AxisCfg {
     static constexpr int CP = C / 2;                                   // float4 column pairs
     static constexpr int NVMAX = L / FftLevels<L>::min_rad();          // most virtual threads any level has
     static constexpr size_t TILE = (size_t)L * CP * sizeof(float4);
-    static constexpr size_t SMEM = (FftLevels<L>::n > 1 ? TILE : 0) + (size_t)TwTable<L>::LEN * sizeof(float2);
+    static constexpr size_t TWB = ((size_t)TwTable<L>::LEN * sizeof(float2) + 15) / 16 * 16;
+    static constexpr size_t SMEM = (FftLevels<L>::n > 1 ? TILE : 0) + TWB + 16;   // tile, twiddle table, mbarrier of the TMA prologue
     static constexpr int WANT = CP * NVMAX;
     static constexpr int TMAX = SMEM > 100 * 1024 ? 512 : 256;
     static constexpr int THREADS = WANT < 32 ? 32 : (WANT > TMAX ? TMAX : WANT);
@@ -50,6 +51,77 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- TMA (cp.async.bulk.tensor) tile prologue
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CUPSS_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CUPSS_MBAR_DONE_%=;\n"
+        "bra CUPSS_MBAR_WAIT_%=;\n"
+        "CUPSS_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// box of the 4-D tensor map at (c0, c1, c2, c3) -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+// plain bulk copy global -> shared on the same barrier (twiddle table)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Tile prologue by TMA, rows in NATURAL order: one elected thread issues a few box loads (tmaBoxRows rows x 128 bytes each)
+// plus the twiddle table; nobody computes an address.  Rows beyond the dealias cut-off (keepLo < row < keepHi) are zero-filled
+// by the threads, row keepLo itself (one 128-byte segment that no box of a power-of-two row count covers) by cp.async.
+// tile_wait_tma returns with the tile complete and visible to every thread of the CTA.
+template <int L, int CP, int THREADS>
+__device__ __forceinline__ void tile_fetch_tma(float4* tile, float2* twS, unsigned long long* bar, const AxisArgs& a, unsigned ct, unsigned b,
+                                               unsigned keepLo, unsigned keepHi, const float2* ibase, bool valid) {
+    constexpr int C = 2 * CP;
+    constexpr unsigned TWBYTES = (unsigned)TwTable<L>::LEN * sizeof(float2);
+    const bool pruned = keepLo < (unsigned)L;
+    const unsigned B = (unsigned)a.tmaBoxRows;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned nbox = pruned ? 2u * (keepLo / B) : (unsigned)L / B;
+        mbar_expect_tx(bar, nbox * B * (unsigned)(CP * sizeof(float4)) + TWBYTES);
+        bulk_load(twS, a.tw, TWBYTES, bar);
+        for (unsigned i = 0; i < nbox; ++i) {
+            // pruned: boxes over [0, keepLo) and [keepHi, L)
+            const unsigned r0 = pruned ? (i < nbox / 2 ? i * B : keepHi + (i - nbox / 2) * B) : i * B;
+            const int v0 = (int)(r0 & (unsigned)a.ain.rpcMask), v1 = (int)(r0 >> a.ain.rpcShift), v2 = (int)b;
+            auto pick = [&](int role) { return role == 0 ? v0 : (role == 1 ? v1 : v2); };
+            tma_load_4d(tile + (size_t)r0 * CP, a.tmap, (int)(ct * C * 2), pick(a.tmaSlot[0]), pick(a.tmaSlot[1]), pick(a.tmaSlot[2]), bar);
+        }
+    }
+    if (pruned) {
+        const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
+        for (unsigned p = keepLo + 1 + tv; p < keepHi; p += THREADS / CP) tile[p * CP + cp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (tv == 0) {
+            if (valid) cp_async16(tile + keepLo * CP + cp, ibase + row_off(a.ain, keepLo));
+            else tile[keepLo * CP + cp] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+    }
+}
+__device__ __forceinline__ void tile_wait_tma(unsigned long long* bar) {
+    cp_async_wait_all();
+    mbar_wait(bar, 0);
+    __syncthreads();
+}
+
 // Level twiddle table -> shared memory with the same asynchronous copies as the tile (no LDG -> STS round trip through
 // registers in front of the first barrier; profiles/r02z: that chain drew 11-14 % of the stall samples of these kernels).
 template <int L, int THREADS>
@@ -79,7 +151,7 @@ __device__ __forceinline__ void tile_fetch(float4* tile, unsigned tv, unsigned c
 // One level over the tile: every real thread walks its virtual threads (v = tv, tv + TV, ...).
 //   ld(pos, frow) -> float4, st(pos, frow, value);  pos = position inside the tile, frow = frequency row that
 //   position holds in the digit-reversed order (only meaningful on the innermost level, M == 1).
-template <int L, int LV, int DIR, int TV, class LdF, class StF>
+template <int L, int LV, int DIR, int TV, bool DIF = (DIR < 0), class LdF, class StF>
 __device__ __forceinline__ void tile_level(unsigned tv, const float2* __restrict__ twS, LdF ld, StF st) {
     using G = LevelGeom<L, LV>;
     constexpr unsigned R = G::R, M = G::M, N = G::N;
@@ -94,7 +166,7 @@ __device__ __forceinline__ void tile_level(unsigned tv, const float2* __restrict
             const float4 t = ld(row0 + M * q, f0 + (L / R) * q);
             x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
         }
-        level_butterfly2<L, LV, DIR, (DIR < 0)>(x0, x1, j, twS);
+        level_butterfly2<L, LV, DIR, DIF>(x0, x1, j, twS);
 #pragma unroll
         for (unsigned q = 0; q < R; ++q) st(row0 + M * q, f0 + (L / R) * q, make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y));
     }
@@ -108,6 +180,7 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     extern __shared__ float4 smem4[];
     float4* tile = smem4;
     float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(twS) + Cfg::TWB);
     const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
     const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = blockIdx.x / (unsigned)a.ncolTiles;
     const unsigned col = ct * C + 2 * cp;
@@ -145,6 +218,17 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     };
     auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
     auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
+    auto fetch_natural = [&]() {   // whole input tile + twiddle table in flight, then wait
+        if (a.tmaOn) {
+            tile_fetch_tma<L, CP, Cfg::THREADS>(tile, twS, bar, a, ct, b, keepLo, keepHi, ibase, valid);
+            tile_wait_tma(bar);
+        } else {
+            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, keepRow);
+            load_twiddles();
+            cp_async_wait_all();
+            __syncthreads();
+        }
+    };
 
     if constexpr (DIR < 0) {   // forward: natural rows in, frequency rows out
         auto gst = [&](unsigned, unsigned frow, float4 v) { gstore(frow, v); };
@@ -152,32 +236,29 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
             auto gld = [&](unsigned pos, unsigned) -> float4 { return gload(pos); };
             tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
         } else {
-            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, keepRow);
-            load_twiddles();
-            cp_async_wait_all();
-            __syncthreads();
+            fetch_natural();
             tile_level<L, 0, DIR, TV>(tv, twS, sld, sst);
             __syncthreads();
             if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
             if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
             tile_level<L, n - 1, DIR, TV>(tv, twS, sld, gst);
         }
-    } else {                   // inverse: frequency rows in, natural rows out
-        auto gst = [&](unsigned pos, unsigned, float4 v) { gstore(pos, v); };
+    } else {
+        // inverse: frequency rows in, in NATURAL order as well (decimation in frequency with the conjugate twiddles), so the
+        // live rows of a pruned transform are two contiguous ranges -- box loads -- and the real-space rows leave permuted
         if constexpr (n == 1) {
+            auto gst1 = [&](unsigned pos, unsigned, float4 v) { gstore(pos, v); };
             auto gld = [&](unsigned, unsigned frow) -> float4 { return masked(gload(frow), frow); };
-            tile_level<L, 0, DIR, TV>(tv, twS, gld, gst);
+            tile_level<L, 0, DIR, TV>(tv, twS, gld, gst1);
         } else {
-            tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return freq_of_pos<L>(p); }, keepRow);
-            load_twiddles();
-            cp_async_wait_all();
+            auto gst = [&](unsigned, unsigned yrow, float4 v) { gstore(yrow, v); };
+            fetch_natural();
+            auto mld = [&](unsigned pos, unsigned) -> float4 { return masked(tile[pos * CP + cp], pos); };
+            tile_level<L, 0, DIR, TV, true>(tv, twS, mld, sst);
             __syncthreads();
-            auto mld = [&](unsigned pos, unsigned frow) -> float4 { return masked(tile[pos * CP + cp], frow); };
-            tile_level<L, n - 1, DIR, TV>(tv, twS, mld, sst);
-            __syncthreads();
-            if constexpr (n >= 4) { tile_level<L, 2, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 3) { tile_level<L, 1, DIR, TV>(tv, twS, sld, sst); __syncthreads(); }
-            tile_level<L, 0, DIR, TV>(tv, twS, sld, gst);
+            if constexpr (n >= 3) { tile_level<L, 1, DIR, TV, true>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 4) { tile_level<L, 2, DIR, TV, true>(tv, twS, sld, sst); __syncthreads(); }
+            tile_level<L, n - 1, DIR, TV, true>(tv, twS, sld, gst);
         }
     }
 }
@@ -193,6 +274,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     extern __shared__ float4 smem4[];
     float4* tile = smem4;
     float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(twS) + Cfg::TWB);
     const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
     const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = blockIdx.x / (unsigned)a.ncolTiles;
     const unsigned col = ct * C + 2 * cp;
@@ -213,18 +295,24 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     float2* lbase = a.out + kbase;
     const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
 
+    const bool tma = n > 1 && a.tmaOn && ks.hasFwd;   // CTA-uniform
     if constexpr (n > 1) {
-        if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
+        if (tma) tile_fetch_tma<L, CP, Cfg::THREADS>(tile, twS, bar, a, ct, b, (unsigned)L, 0u, ibase, valid);
+        else if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
     }
-    tw_fetch<L, Cfg::THREADS>(twS, a.tw);
+    if (!tma) tw_fetch<L, Cfg::THREADS>(twS, a.tw);
     if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
         // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
         const float2* p0 = ks.src[0] + (b * (unsigned)a.aout.bs + ct * C);
         for (unsigned r = threadIdx.x; r < (unsigned)L; r += Cfg::THREADS)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + r * krs));
     }
-    cp_async_wait_all();
-    __syncthreads();
+    if (tma) {
+        tile_wait_tma(bar);
+    } else {
+        cp_async_wait_all();
+        __syncthreads();
+    }
 
     auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
     auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };

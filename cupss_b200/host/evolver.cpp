@@ -255,6 +255,7 @@ void evolver::prepareProblem() {
         for (term *t : f->terms) t->prepareDevice();
         const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;   // this rank's z-slab of the full host array
         engineCheck(cupss_b200_upload_real(plan, f->engine_id, reinterpret_cast<const float *>(f->real_array + slab)), "upload_real");
+        f->mirror_in_sync = true;
     }
     if (verbose) std::cout << "Building the fused per-equation plan." << std::endl;
     sendSystemToEngine();
@@ -325,6 +326,7 @@ int evolver::advanceTime() {
     if (planDirty) sendSystemToEngine();
     bool anyCB = false;
     for (field *f : fields) anyCB = anyCB || f->hasCB || f->hasCBFourier;
+    for (field *f : fields) f->mirror_in_sync = false;
     if (!anyCB) {
         engineCheck(cupss_b200_step(plan, 1), "step");
     } else {
@@ -346,7 +348,10 @@ int evolver::advanceTime() {
 void evolver::refreshHostMirror(field *f, bool real_part, bool comp_part) {
     if (!plan || f->engine_id < 0) return;
     const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;
-    if (real_part) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array + slab)), "download_real");
+    // Until the first step after an upload the host real array is the device state bit for bit (the reference's real_array_d is
+    // a plain copy of it, src/field_init.cpp; writeOut at step 0 prints the initial condition exactly); the engine only keeps
+    // the spectrum, and spectrum -> real would return the same values with 1e-7 of round-off on top.
+    if (real_part && !f->mirror_in_sync) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array + slab)), "download_real");
     // partitioned: collective (every rank calls it); each rank receives the kz planes of its own z-slab of the full spectrum
     if (comp_part) engineCheck(cupss_b200_download_comp(plan, f->engine_id, reinterpret_cast<float *>(f->comp_array + slab)), "download_comp");
 }
@@ -357,6 +362,7 @@ void evolver::uploadHostMirror(field *f) {
     if (!plan || f->engine_id < 0) return;   // before prepareProblem the host arrays ARE the state
     const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;
     engineCheck(cupss_b200_upload_real(plan, f->engine_id, reinterpret_cast<const float *>(f->real_array + slab)), "upload_real");
+    f->mirror_in_sync = true;
 }
 
 void evolver::writeOut() {

@@ -26,6 +26,8 @@ class field {
     int integrator = EULER;
     evolver *system_p = nullptr;
     int engine_id = -1;   // id inside the engine plan
+    bool mirror_in_sync = false;   // real_array was uploaded and no step ran since: it IS the device state, exactly (what the
+                                   // reference's real_array_d holds at that point), so a download must not round-trip it
 
     // host mirrors, float2[sz*sy*sx] row-major [z][y][x], value in .x
     float2 *real_array;
