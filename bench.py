@@ -406,7 +406,12 @@ def quick_parity(name, n, steps, Evolver):
         nw = float(np.linalg.norm(w))
         errs[f] = float(np.linalg.norm(out["got"][f].astype(np.float64) - w) / (nw if nw > 0 else 1.0))
     worst = max(errs.values())
-    return {"ok": bool(worst < PARITY_TOL), "steps": steps, "grid": n, "rel_l2_max": worst, "rel_l2": errs, "tol": PARITY_TOL,
+    # Model H: the projected velocity and its curl are differences of nearly equal terms; no float32 pipeline agrees with another
+    # to 1e-5 on them (tests/golden/f32_floor.py: numpy float32 vs float64 2.4e-5 / 4.0e-5 / 1.4e-4 on vx / vy / w, 1e-5 on the
+    # stresses) -- same per-field tolerances as tests/cases.py::modelh_256; the dynamic field and its gradients keep 1e-5
+    tols = dict(sigxx=1.5e-5, sigxy=1.5e-5, P=1.5e-5, vx=3.6e-5, vy=6e-5, w=2.1e-4) if name == "modelh" else {}
+    ok = all(e < tols.get(f, PARITY_TOL) for f, e in errs.items())
+    return {"ok": bool(ok), "steps": steps, "grid": n, "rel_l2_max": worst, "rel_l2": errs, "tol": PARITY_TOL, "tol_per_field": tols or None,
             "against": "oracle/_ref/libcupss_ref_f.so (reference CPU path with the GPU kernels' semantics) on the same grid and input"}
 
 

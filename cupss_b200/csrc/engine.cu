@@ -159,7 +159,7 @@ static bool jit_load() {
 static std::string jit_source(const cupss::KStageD& ks, int L) {
     using namespace cupss;
     std::string s = "#include \"kernels_axis.cuh\"\nnamespace cupss {\nstruct JitPlan {\n";
-    char b[256];
+    char b[512];
     int npres = 0, nterm = 0;
     for (int o = 0; o < ks.nout; ++o) {
         nterm = std::max(nterm, ks.out[o].termOff + ks.out[o].nterm);
@@ -188,7 +188,11 @@ static std::string jit_source(const cupss::KStageD& ks, int L) {
         s += b;
     }
     s += "        }\n        return PlanPres{};\n    }\n};\n}  // namespace cupss\n";
-    snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(cupss::AxisCfg<%d>::THREADS, cupss::AxisCfg<%d>::MINB)\n", L, L);
+    // cluster-shared axes: at most 2 CTAs per SM like the library's k-stage kernels (128 registers per thread; measured on Model H
+    // 2048^2: 0.097 ms against 0.50 ms with the 85-register cap of 3 CTAs per SM).  Single-CTA axes keep 3 CTAs per SM: the noisy
+    // KPZ-3D 512^3 k stage runs 0.81 ms that way against 0.98 ms at 2 (profiles/README.md, r2e / r2f).
+    if (cupss::axis_cluster_size(L) > 1) snprintf(b, sizeof b, "extern \"C\" __global__ void __cluster_dims__(cupss::AxisCfg<%d>::CL, 1, 1) __launch_bounds__(cupss::AxisCfg<%d>::THREADS, (cupss::AxisCfg<%d>::MINB > 2 ? 2 : cupss::AxisCfg<%d>::MINB))\n", L, L, L, L);
+    else snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(cupss::AxisCfg<%d>::THREADS, cupss::AxisCfg<%d>::MINB)\n", L, L);
     s += b;
     s += "jit_kstage(const __grid_constant__ cupss::AxisArgs a, const __grid_constant__ cupss::KStageD ks) {\n";
     snprintf(b, sizeof b, "    cupss::axis_kstage_body<%d, cupss::KS_JIT, -1, cupss::JitPlan>(a, ks);\n}\n", L);
@@ -266,7 +270,7 @@ static TensorMapEncodeTiledFn tensor_map_encoder() {
 static void prepare_tma(cupss::AxisArgs& a, int L, bool kstage) {
     a.tmaOn = 0;
     TensorMapEncodeTiledFn enc = tensor_map_encoder();
-    if (!enc || L < 32 || !a.in) return;
+    if (!enc || L < 32 || !a.in || cupss::axis_cluster_size(L) > 1) return;   // cluster kernels load rows inside their cross level
     const int C = cupss::axis_tile_cols(L);
     const long long rpc = (long long)a.ain.rpcMask + 1, nchunk = L / rpc;
     int B = L < 256 ? L : 256;
@@ -417,6 +421,27 @@ struct cupss_b200_plan {
         *out = d;
         return CUPSS_B200_OK;
     }
+    // Twiddles of a strided-axis pass over L rows: the level table of the transform one CTA runs and, when a cluster shares
+    // the axis, the table of the level that couples the CTAs' blocks (key 1000000 + L in the same cache).
+    int get_axis_twiddles(int L, AxisArgs& a) {
+        a.twX = nullptr;
+        const int CL = axis_cluster_size(L);
+        if (CL <= 1) return get_twiddle(L, &a.tw);
+        CKR(get_twiddle(axis_cta_rows(L), &a.tw));
+        auto it = twiddles.find(1000000 + L);
+        if (it == twiddles.end()) {
+            std::vector<float2> h((size_t)L);
+            const int nent = host_cross_twiddles(L, h.data());
+            if (nent <= 0) return fail(CUPSS_B200_ERR_ARG, "unsupported transform length %d", L);
+            float2* d = nullptr;
+            CK(cudaMalloc(&d, sizeof(float2) * (size_t)nent));
+            CK(cudaMemcpyAsync(d, h.data(), sizeof(float2) * (size_t)nent, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+            it = twiddles.emplace(1000000 + L, d).first;
+        }
+        a.twX = it->second;
+        return CUPSS_B200_OK;
+    }
     // twiddles of the two-level x kernel (key -sx in the same cache); *out = nullptr when that kernel does not cover sx
     int get_twiddle_x3(const float2** out) {
         *out = nullptr;
@@ -465,7 +490,7 @@ struct cupss_b200_plan {
         else { n.bs = 0; n.rs = 0; a.nbatch = 1; a.axis = 0; }
         n.cs = 0; n.rpcShift = ilog2(*L); n.rpcMask = *L - 1;
         a.ain = n; a.aout = n;
-        return get_twiddle(*L, &a.tw);
+        return get_axis_twiddles(*L, a);
     }
     // y pass of a 3-D transform: natural side [z_local][y][pitch], exchange side [peer][z_local][ky_local][pitch]
     int make_y_axis(AxisArgs& a, bool forward) {
@@ -476,7 +501,7 @@ struct cupss_b200_plan {
         exc.bs = (long long)kyl * pitch; exc.rs = pitch; exc.cs = (long long)zl * kyl * pitch;
         exc.rpcShift = ilog2(kyl); exc.rpcMask = kyl - 1;
         if (forward) { a.ain = nat; a.aout = exc; } else { a.ain = exc; a.aout = nat; }
-        return get_twiddle(sy, &a.tw);
+        return get_axis_twiddles(sy, a);
     }
 
     int add_a2a(std::vector<Launch>& out, const char* nm, const float2* send, float2* recv) {
@@ -596,7 +621,7 @@ struct cupss_b200_plan {
                     size_t smem = 0;
                     axis_kstage_geometry(l.L, &threads, &smem, &minb);
                     void* params[] = {&l.ax, &l.ks};
-                    const unsigned grid = (unsigned)l.ax.ncolTiles * (unsigned)l.ax.nbatch;
+                    const unsigned grid = (unsigned)l.ax.ncolTiles * (unsigned)l.ax.nbatch * (unsigned)axis_cluster_size(l.L);
                     const int rc = g_jit.LaunchKernel(l.jitFn, grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, stream, params, nullptr);
                     if (rc != 0) return fail(CUPSS_B200_ERR_CUDA, "cuLaunchKernel of the plan-specialised k stage failed (%d)", rc);
                 } else {

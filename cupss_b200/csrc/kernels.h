@@ -26,7 +26,8 @@ struct AxisArgs {
     int ncolTiles;   // column tiles of THIS launch (ceil(ncol / C) unless the pass is split into column chunks)
     int ctBase;      // first column tile of this launch (column-chunked exchange pipeline, engine.cu)
     int nbatch;
-    const float2* tw;
+    const float2* tw;    // level twiddle table of the transform a CTA runs (fft_core.cuh; 512 points when a cluster shares the axis)
+    const float2* twX;   // cluster kernels: (CL-1) x 512 twiddles of the level that couples the CTAs' blocks, else null
     int axis;        // k index carried by the rows: 1 = ky, 2 = kz, 0 = none (L = 1)
     int kyBase;      // axis == 2: iky = kyBase + batch
     int maskOn, cutx, cuty, cutz;   // plain inverse: dealias mask applied on load
@@ -116,6 +117,11 @@ int axis_tile_cols(int L);          // C used for length L
 bool axis_kstage_geometry(int L, int* threads, size_t* smem, int* minBlocks);
 // Level twiddle table of an L-point transform (fft_core.cuh); returns the number of entries written (<= L), 0 if unsupported.
 int host_level_twiddles(int L, float2* out);
+// Long axes shared by a thread-block cluster (kernels_axis.cuh: AxisCfg): CTAs per cluster (1: none), rows per CTA, and the
+// (CL-1) x rows table of the level that couples the CTAs' blocks (returns the number of entries, 0 without a cluster).
+int axis_cluster_size(int L);
+int axis_cta_rows(int L);
+int host_cross_twiddles(int L, float2* out);
 // Two-level x pass (kernels_x3.cu): sizes it covers, its twiddle table (<= sx entries) and its launcher.
 bool xpass3_supported(int sx);
 int host_x3_twiddles(int sx, float2* out);

@@ -67,66 +67,79 @@ static cudaError_t set_smem(K kernel, size_t smem) {
 
 template <int L>
 static cudaError_t launch_plain_L(int dir, const AxisArgs& a, cudaStream_t st) {
+    using Cfg = AxisCfg<L>;
+    constexpr bool CLUSTER = Cfg::CL > 1;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = set_smem(axis_plain_kernel<L, -1, false>, AxisCfg<L>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = set_smem(axis_plain_kernel<L, 1, false>, AxisCfg<L>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = set_smem(axis_plain_kernel<L, 1, true>, AxisCfg<L>::SMEM);
+        cudaError_t e = cudaSuccess;
+        if constexpr (CLUSTER) {
+            e = set_smem(axis_plain_cluster_kernel<L, -1, false>, Cfg::SMEM);
+            if (e == cudaSuccess) e = set_smem(axis_plain_cluster_kernel<L, 1, false>, Cfg::SMEM);
+            if (e == cudaSuccess) e = set_smem(axis_plain_cluster_kernel<L, 1, true>, Cfg::SMEM);
+        } else {
+            e = set_smem(axis_plain_kernel<L, -1, false>, Cfg::SMEM);
+            if (e == cudaSuccess) e = set_smem(axis_plain_kernel<L, 1, false>, Cfg::SMEM);
+            if (e == cudaSuccess) e = set_smem(axis_plain_kernel<L, 1, true>, Cfg::SMEM);
+        }
         if (e != cudaSuccess) return e;
         attr = true;
     }
     // pruned inverse passes: column tiles beyond the dealias cut-off produce nothing -- they are not launched at all
     AxisArgs la = a;
     if (a.pruneOn && dir > 0) {
-        const int live = a.pruneCutX / AxisCfg<L>::C + 1 - a.ctBase;   // live tiles of this launch's column chunk
+        const int live = a.pruneCutX / Cfg::C + 1 - a.ctBase;   // live tiles of this launch's column chunk
         if (live <= 0) return cudaSuccess;
         if (live < la.ncolTiles) la.ncolTiles = live;
     }
-    const unsigned grid = (unsigned)la.ncolTiles * (unsigned)la.nbatch;
+    const unsigned grid = (unsigned)la.ncolTiles * (unsigned)la.nbatch * (unsigned)Cfg::CL;   // CL CTAs (one cluster) per tile
     if (grid == 0) return cudaSuccess;
-    if (dir < 0) {
-        if (a.maskOn) return cudaErrorInvalidValue;   // the mask only exists on inverse transforms
-        axis_plain_kernel<L, -1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);
-    } else if (a.maskOn) {
-        axis_plain_kernel<L, 1, true><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);
+    if (dir < 0 && a.maskOn) return cudaErrorInvalidValue;   // the mask only exists on inverse transforms
+    if constexpr (CLUSTER) {
+        if (dir < 0) axis_plain_cluster_kernel<L, -1, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(la);
+        else if (a.maskOn) axis_plain_cluster_kernel<L, 1, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(la);
+        else axis_plain_cluster_kernel<L, 1, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(la);
     } else {
-        axis_plain_kernel<L, 1, false><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(la);
+        if (dir < 0) axis_plain_kernel<L, -1, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(la);
+        else if (a.maskOn) axis_plain_kernel<L, 1, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(la);
+        else axis_plain_kernel<L, 1, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(la);
+    }
+    return cudaGetLastError();
+}
+
+template <int L, int KIND, int SIG>
+static cudaError_t launch_kstage_variant(unsigned grid, const AxisArgs& a, const KStageD& ks, cudaStream_t st) {
+    using Cfg = AxisCfg<L>;
+    static bool attr = false;
+    if constexpr (Cfg::CL > 1) {
+        if (!attr) {
+            cudaError_t e = set_smem(axis_kstage_cluster_kernel<L, KIND, SIG>, Cfg::SMEM);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        axis_kstage_cluster_kernel<L, KIND, SIG><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, ks);
+    } else {
+        if (!attr) {
+            cudaError_t e = set_smem(axis_kstage_kernel<L, KIND, SIG>, Cfg::SMEM);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        axis_kstage_kernel<L, KIND, SIG><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, ks);
     }
     return cudaGetLastError();
 }
 
 template <int L>
 static cudaError_t launch_kstage_L(const AxisArgs& a, const KStageD& ks, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = set_smem(axis_kstage_kernel<L, KS_GENERIC, -1>, AxisCfg<L>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = set_smem(axis_kstage_kernel<L, KS_SCALAR_Q2, -1>, AxisCfg<L>::SMEM);
-        if (e != cudaSuccess) return e;
-        if constexpr (L >= 64) {
-            e = set_smem(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD>, AxisCfg<L>::SMEM);
-            if (e != cudaSuccess) return e;
-            e = set_smem(axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION>, AxisCfg<L>::SMEM);
-            if (e != cudaSuccess) return e;
-        }
-        attr = true;
-    }
-    const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch;
+    const unsigned grid = (unsigned)a.ncolTiles * (unsigned)a.nbatch * (unsigned)AxisCfg<L>::CL;
     if (ks.fastKind == KS_SCALAR_Q2) {
         const int sig = sq2_signature(ks.sq2);
-        if (L >= 64 && sig == SQ2_SIG_CAHN_HILLIARD) {
-            if constexpr (L >= 64) axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
-        } else if (L >= 64 && sig == SQ2_SIG_DIFFUSION) {
-            if constexpr (L >= 64) axis_kstage_kernel<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
-        } else {
-            axis_kstage_kernel<L, KS_SCALAR_Q2, -1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+        if constexpr (L >= 64) {
+            if (sig == SQ2_SIG_CAHN_HILLIARD) return launch_kstage_variant<L, KS_SCALAR_Q2, SQ2_SIG_CAHN_HILLIARD>(grid, a, ks, st);
+            if (sig == SQ2_SIG_DIFFUSION) return launch_kstage_variant<L, KS_SCALAR_Q2, SQ2_SIG_DIFFUSION>(grid, a, ks, st);
         }
-    } else {
-        axis_kstage_kernel<L, KS_GENERIC, -1><<<grid, AxisCfg<L>::THREADS, AxisCfg<L>::SMEM, st>>>(a, ks);
+        return launch_kstage_variant<L, KS_SCALAR_Q2, -1>(grid, a, ks, st);
     }
-    return cudaGetLastError();
+    return launch_kstage_variant<L, KS_GENERIC, -1>(grid, a, ks, st);
 }
 
 #define CUPSS_FOR_SIZES(X) X(1) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
@@ -167,6 +180,34 @@ bool axis_kstage_geometry(int L, int* threads, size_t* smem, int* minBlocks) {
 #undef X
     }
     return false;
+}
+
+int axis_cluster_size(int L) {
+    switch (L) {
+#define X(N) case N: return AxisCfg<N>::CL;
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return 1;
+}
+int axis_cta_rows(int L) {
+    switch (L) {
+#define X(N) case N: return AxisCfg<N>::LS;
+        CUPSS_FOR_SIZES(X)
+#undef X
+    }
+    return L;
+}
+// (CL-1) x S table of the level that couples the blocks of a cluster: entry (c-1) S + j = exp(-2 pi i j c / L)
+int host_cross_twiddles(int L, float2* out) {
+    const int CL = axis_cluster_size(L), S = axis_cta_rows(L);
+    if (CL <= 1) return 0;
+    for (int c = 1; c < CL; ++c)
+        for (int j = 0; j < S; ++j) {
+            const double ang = -2.0 * kPi * (double)(((long long)j * c) % L) / (double)L;
+            out[(c - 1) * S + j] = make_float2((float)__builtin_cos(ang), (float)__builtin_sin(ang));
+        }
+    return (CL - 1) * S;
 }
 
 int host_level_twiddles(int L, float2* out) {

@@ -5,13 +5,20 @@
 
 namespace cupss {
 
+// Long axes (1024, 2048, 4096 rows) are shared by a thread-block cluster of CL = L / 512 CTAs: every CTA keeps 512 rows x 16
+// columns of the tile in its own shared memory (the geometry of the 512-point kernels: 128-byte row segments, 64 KB per CTA,
+// 2-3 CTAs per SM), and the one level of the transform that couples the blocks runs over distributed shared memory
+// (cross_scatter / cross_gather below).  Without a cluster a 4096-row tile fits one SM's shared memory only 4 columns wide
+// (32-byte segments, one CTA per SM): 29 % of the HBM roofline on Cahn-Hilliard 2-D 4096^2 (profiles/r2a_bench.json).
 template <int L> struct AxisCfg {
-    static constexpr int C = L <= 512 ? 16 : (L <= 2048 ? 8 : (L <= 4096 ? 4 : 2));
+    static constexpr int CL = (L >= 1024 && L <= 4096) ? L / 512 : 1;   // CTAs per cluster
+    static constexpr int LS = L / CL;                                   // rows per CTA
+    static constexpr int C = LS <= 512 ? 16 : (LS <= 2048 ? 8 : (LS <= 4096 ? 4 : 2));
     static constexpr int CP = C / 2;                                   // float4 column pairs
-    static constexpr int NVMAX = L / FftLevels<L>::min_rad();          // most virtual threads any level has
-    static constexpr size_t TILE = (size_t)L * CP * sizeof(float4);
-    static constexpr size_t TWB = ((size_t)TwTable<L>::LEN * sizeof(float2) + 15) / 16 * 16;
-    static constexpr size_t SMEM = (FftLevels<L>::n > 1 ? TILE : 0) + TWB + 16;   // tile, twiddle table, mbarrier of the TMA prologue
+    static constexpr int NVMAX = LS / FftLevels<LS>::min_rad();        // most virtual threads any level has
+    static constexpr size_t TILE = (size_t)LS * CP * sizeof(float4);
+    static constexpr size_t TWB = ((size_t)TwTable<LS>::LEN * sizeof(float2) + 15) / 16 * 16;
+    static constexpr size_t SMEM = (FftLevels<LS>::n > 1 ? TILE : 0) + TWB + 16;   // tile, twiddle table, mbarrier of the TMA prologue
     static constexpr int WANT = CP * NVMAX;
     static constexpr int TMAX = SMEM > 100 * 1024 ? 512 : 256;
     static constexpr int THREADS = WANT < 32 ? 32 : (WANT > TMAX ? TMAX : WANT);
@@ -120,6 +127,92 @@ __device__ __forceinline__ void tile_wait_tma(unsigned long long* bar) {
     cp_async_wait_all();
     mbar_wait(bar, 0);
     __syncthreads();
+}
+
+// ---------------------------------------------------------------- thread-block clusters: the level that couples the CTAs' blocks
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned dsmem_addr(unsigned localAddr, unsigned ctaRank) {   // same offset in CTA `ctaRank` of the cluster
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(localAddr), "r"(ctaRank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_dsmem4(unsigned addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// First level of a decimation-in-frequency transform of L = CL * S rows held S rows per CTA (natural row order): a radix-CL
+// butterfly over rows j, j + S, ..., j + (CL-1) S, the twiddle w_L^(j c), and output c goes to row j of CTA c's tile.  CTA
+// `crank` does this for its slice of S / CL values of j, reading the CL rows straight from global memory (`gld`, whole
+// 128-byte segments) and scattering over distributed shared memory: per CTA one tile in, one tile out, whatever CL is.
+// Afterwards CTA c holds the S-point sequence whose transform is the frequencies c, c + CL, c + 2 CL, ...
+// twX: (CL-1) x S table, entry (c-1) S + j = exp(-2 pi i j c / L).
+template <int L, int CL, int SIGN, int CP, int TV, class LdRow>
+__device__ __forceinline__ void cross_scatter(float4* tile, unsigned crank, unsigned tv, unsigned cp, const float2* __restrict__ twX, LdRow gld) {
+    constexpr unsigned S = L / CL, JS = S / CL;
+    const unsigned base = smem_u32(tile);
+#pragma unroll 1
+    for (unsigned jj = tv; jj < JS; jj += TV) {
+        const unsigned j = crank * JS + jj;
+        float2 x0[CL], x1[CL];
+#pragma unroll
+        for (unsigned q = 0; q < (unsigned)CL; ++q) {
+            const float4 t = gld(j + S * q);
+            x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
+        }
+        Dft<CL, SIGN>::run(x0);
+        Dft<CL, SIGN>::run(x1);
+#pragma unroll
+        for (unsigned c = 1; c < (unsigned)CL; ++c) {
+            const float2 w = __ldg(twX + (c - 1) * S + j);
+            x0[c] = SIGN > 0 ? cmul_conj(x0[c], w) : cmul(x0[c], w);
+            x1[c] = SIGN > 0 ? cmul_conj(x1[c], w) : cmul(x1[c], w);
+        }
+        const unsigned off = base + (j * CP + cp) * (unsigned)sizeof(float4);
+#pragma unroll
+        for (unsigned c = 0; c < (unsigned)CL; ++c) st_dsmem4(dsmem_addr(off, c), make_float4(x0[c].x, x0[c].y, x1[c].x, x1[c].y));
+    }
+}
+// Last level of the matching decimation-in-time inverse: CTA c holds (natural order) the inverse S-point transform of the
+// frequencies congruent to c; row j of every CTA is gathered, twiddled by conj w_L^(j c) and butterflied into the real-space
+// rows j, j + S, ..., which `gst` stores to global memory (or pushes to the peer that owns them).
+template <int L, int CL, int CP, int TV, class StRow>
+__device__ __forceinline__ void cross_gather(const float4* tile, unsigned crank, unsigned tv, unsigned cp, const float2* __restrict__ twX, StRow gst) {
+    constexpr unsigned S = L / CL, JS = S / CL;
+    const unsigned base = smem_u32(tile);
+#pragma unroll 1
+    for (unsigned jj = tv; jj < JS; jj += TV) {
+        const unsigned j = crank * JS + jj;
+        const unsigned off = base + (j * CP + cp) * (unsigned)sizeof(float4);
+        float2 x0[CL], x1[CL];
+#pragma unroll
+        for (unsigned c = 0; c < (unsigned)CL; ++c) {
+            const float4 t = ld_dsmem4(dsmem_addr(off, c));
+            x0[c] = make_float2(t.x, t.y); x1[c] = make_float2(t.z, t.w);
+        }
+#pragma unroll
+        for (unsigned c = 1; c < (unsigned)CL; ++c) {
+            const float2 w = __ldg(twX + (c - 1) * S + j);
+            x0[c] = cmul_conj(x0[c], w);
+            x1[c] = cmul_conj(x1[c], w);
+        }
+        Dft<CL, +1>::run(x0);
+        Dft<CL, +1>::run(x1);
+#pragma unroll
+        for (unsigned q = 0; q < (unsigned)CL; ++q) gst(j + S * q, make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y));
+    }
 }
 
 // Level twiddle table -> shared memory with the same asynchronous copies as the tile (no LDG -> STS round trip through
@@ -263,20 +356,79 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     }
 }
 
+// Same pass for an axis shared by a cluster (AxisCfg<L>::CL > 1); both directions run decimation in frequency from natural
+// row order: cross level (global loads -> distributed shared memory), then the 512-point levels on the CTA's own block.  The
+// block of CTA c ends with position p holding output row c + CL * freq_of_pos<512>(p).
+template <int L, int DIR, bool MASK>
+__global__ void __cluster_dims__(AxisCfg<L>::CL, 1, 1) __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB)
+axis_plain_cluster_kernel(const __grid_constant__ AxisArgs a) {
+    using Cfg = AxisCfg<L>;
+    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, CL = Cfg::CL, S = Cfg::LS, n = FftLevels<S>::n;
+    static_assert(CL > 1 && n >= 2, "cluster kernel");
+    extern __shared__ float4 smem4[];
+    float4* tile = smem4;
+    float2* twS = reinterpret_cast<float2*>(smem4 + (size_t)S * CP);
+    const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
+    const unsigned crank = cluster_ctarank(), tileId = blockIdx.x / CL;
+    const unsigned ct = tileId % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = tileId / (unsigned)a.ncolTiles;
+    const unsigned col = ct * C + 2 * cp;
+    const bool valid = col < (unsigned)a.ncol;
+
+    if (a.pruneOn) {   // cluster-uniform: the whole tile is outside the dealias cut-off -> output stays zero
+        const int iyT = a.kyBase + (int)b;
+        const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
+        if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
+    }
+    const float2* ibase = a.in + (b * (unsigned)a.ain.bs + col);
+    float2* lbase = a.out + (b * (unsigned)a.aout.bs + col);
+    const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
+    const unsigned keepLo = a.rowCut >= 0 ? (unsigned)a.rowCut : (unsigned)L, keepHi = a.rowCut >= 0 ? (unsigned)(L - a.rowCut) : 0u;
+    auto gld = [&](unsigned row) -> float4 {
+        if (!(valid && (row <= keepLo || row >= keepHi))) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 t = ld4(ibase + row_off(a.ain, row));
+        if constexpr (MASK) {
+            const int iy = a.axis == 2 ? a.kyBase + (int)b : (a.axis == 1 ? (int)row : 0);
+            const int iz = a.axis == 2 ? (int)row : 0;
+            if (!dealias_keep((int)col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.x = 0.0f; t.y = 0.0f; }
+            if (!dealias_keep((int)col + 1, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.z = 0.0f; t.w = 0.0f; }
+        }
+        return t;
+    };
+    auto gst = [&](unsigned, unsigned frow, float4 v) {   // frow: local frequency of the 512-point transform
+        if (valid) st4(axis_dst(a, lbase, pbase, crank + (unsigned)CL * frow), v);
+    };
+    auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
+    auto sst = [&](unsigned pos, unsigned, float4 v) { tile[pos * CP + cp] = v; };
+
+    tw_fetch<S, Cfg::THREADS>(twS, a.tw);
+    cluster_sync();   // every CTA of the cluster is running: its shared memory may be written
+    cross_scatter<L, CL, DIR, CP, TV>(tile, crank, tv, cp, a.twX, gld);
+    cp_async_wait_all();
+    cluster_sync();   // all blocks complete (also a CTA barrier)
+    tile_level<S, 0, DIR, TV, true>(tv, twS, sld, sst);
+    __syncthreads();
+    if constexpr (n >= 3) { tile_level<S, 1, DIR, TV, true>(tv, twS, sld, sst); __syncthreads(); }
+    tile_level<S, n - 1, DIR, TV, true>(tv, twS, sld, gst);
+}
+
 // PLAN: compile-time structure of the sweep for KIND == KS_JIT (kstage.cuh), void otherwise.
+// A cluster-shared axis (AxisCfg<L>::CL > 1): the CTA runs the S = 512-point levels on its own block between the two cross
+// levels; position p of CTA c's block holds frequency row c + CL * freq_of_pos<S>(p), so with q unrolled the row of the
+// fused level is still "f0 + (L / R) q" with f0 < L / R -- the per-mode code below is the same for both geometries.
 template <int L, int KIND, int SIG, class PLAN>
 __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStageD& ks) {
     using Cfg = AxisCfg<L>;
-    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, n = FftLevels<L>::n;
+    constexpr int C = Cfg::C, CP = Cfg::CP, TV = Cfg::TV, CL = Cfg::CL, S = Cfg::LS, n = FftLevels<S>::n;
     constexpr int LAST = n - 1;
-    using G = LevelGeom<L, LAST>;
+    using G = LevelGeom<S, LAST>;
     constexpr unsigned R = G::R;
     extern __shared__ float4 smem4[];
     float4* tile = smem4;
-    float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)L * CP : 0));
+    float2* twS = reinterpret_cast<float2*>(smem4 + (n > 1 ? (size_t)S * CP : 0));
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(twS) + Cfg::TWB);
     const unsigned cp = threadIdx.x % CP, tv = threadIdx.x / CP;
-    const unsigned ct = blockIdx.x % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = blockIdx.x / (unsigned)a.ncolTiles;
+    const unsigned crank = CL > 1 ? cluster_ctarank() : 0u, tileId = blockIdx.x / (unsigned)CL;
+    const unsigned ct = tileId % (unsigned)a.ncolTiles + (unsigned)a.ctBase, b = tileId / (unsigned)a.ncolTiles;
     const unsigned col = ct * C + 2 * cp;
     const bool valid = col < (unsigned)a.ncol, valid1 = col + 1 < (unsigned)a.ncol;
 
@@ -295,23 +447,31 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     float2* lbase = a.out + kbase;
     const unsigned long long pbase = (unsigned long long)a.pushBase + (unsigned long long)b * (unsigned long long)a.pushBs + col;
 
-    const bool tma = n > 1 && a.tmaOn && ks.hasFwd;   // CTA-uniform
-    if constexpr (n > 1) {
+    const bool tma = CL == 1 && n > 1 && a.tmaOn && ks.hasFwd;   // CTA-uniform
+    if constexpr (CL > 1) {
+        // cross level of the forward transform: rows straight from global memory, butterflied and scattered over the cluster
+        tw_fetch<S, Cfg::THREADS>(twS, a.tw);
+        cluster_sync();
+        if (ks.hasFwd)
+            cross_scatter<L, CL, -1, CP, TV>(tile, crank, tv, cp, a.twX, [&](unsigned row) -> float4 {
+                return valid ? ld4(ibase + row_off(a.ain, row)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            });
+    } else if constexpr (n > 1) {
         if (tma) tile_fetch_tma<L, CP, Cfg::THREADS>(tile, twS, bar, a, ct, b, (unsigned)L, 0u, ibase, valid);
         else if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
     }
-    if (!tma) tw_fetch<L, Cfg::THREADS>(twS, a.tw);
+    if (CL == 1 && !tma) tw_fetch<S, Cfg::THREADS>(twS, a.tw);
     if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
         // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
         const float2* p0 = ks.src[0] + (b * (unsigned)a.aout.bs + ct * C);
-        for (unsigned r = threadIdx.x; r < (unsigned)L; r += Cfg::THREADS)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + r * krs));
+        for (unsigned r = threadIdx.x; r < (unsigned)S; r += Cfg::THREADS)   // the rows this CTA's block will hold: crank + CL r
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (crank + (unsigned)CL * r) * krs));
     }
     if (tma) {
         tile_wait_tma(bar);
     } else {
         cp_async_wait_all();
-        __syncthreads();
+        if constexpr (CL > 1) cluster_sync(); else __syncthreads();
     }
 
     auto sld = [&](unsigned pos, unsigned) -> float4 { return tile[pos * CP + cp]; };
@@ -320,10 +480,10 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     // ---- forward levels 0 .. n-2 (the last level is fused with the k stage below)
     if (ks.hasFwd) {
         if constexpr (n > 1) {
-            tile_level<L, 0, -1, TV>(tv, twS, sld, sst);
+            tile_level<S, 0, -1, TV>(tv, twS, sld, sst);
             __syncthreads();
-            if constexpr (n >= 3) { tile_level<L, 1, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 4) { tile_level<L, 2, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 3) { tile_level<S, 1, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 4) { tile_level<S, 2, -1, TV>(tv, twS, sld, sst); __syncthreads(); }
         }
     }
 
@@ -350,7 +510,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     // ---- fused level: last forward butterfly -> k stage -> first inverse butterfly
 #pragma unroll 1
     for (unsigned v = tv; v < (unsigned)G::NV; v += TV) {
-        const unsigned f0 = freq_of_pos<L>(v * R);
+        const unsigned f0 = crank + (unsigned)CL * freq_of_pos<S>(v * R);
         float2 x0[R], x1[R];
         // state rows of this virtual thread: issued before the butterfly so that their (L2) latency overlaps it
         const unsigned rowStride = (L / R) * krs;
@@ -370,7 +530,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                 else t = valid ? ld4(ibase + row_off(a.ain, v * R + q)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 x0[q] = make_float2(t.x, t.y); x1[q] = make_float2(t.z, t.w);
             }
-            level_butterfly2<L, LAST, -1, true>(x0, x1, 0, twS);
+            level_butterfly2<S, LAST, -1, true>(x0, x1, 0, twS);
         } else {
 #pragma unroll
             for (unsigned q = 0; q < R; ++q) { x0[q] = make_float2(0.0f, 0.0f); x1[q] = make_float2(0.0f, 0.0f); }
@@ -445,7 +605,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
         }
 
         if (doInv) {
-            level_butterfly2<L, LAST, +1, false>(x0, x1, 0, twS);
+            level_butterfly2<S, LAST, +1, false>(x0, x1, 0, twS);
 #pragma unroll
             for (unsigned q = 0; q < R; ++q) {
                 const float4 t = make_float4(x0[q].x, x0[q].y, x1[q].x, x1[q].y);
@@ -462,16 +622,30 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                 if (valid) st4(axis_dst(a, lbase, pbase, pos), v);
             };
             __syncthreads();
-            if constexpr (n >= 4) { tile_level<L, 2, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
-            if constexpr (n >= 3) { tile_level<L, 1, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
-            tile_level<L, 0, +1, TV>(tv, twS, sld, gst);
+            if constexpr (n >= 4) { tile_level<S, 2, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (n >= 3) { tile_level<S, 1, +1, TV>(tv, twS, sld, sst); __syncthreads(); }
+            if constexpr (CL == 1) {
+                tile_level<S, 0, +1, TV>(tv, twS, sld, gst);
+            } else {
+                tile_level<S, 0, +1, TV>(tv, twS, sld, sst);
+                cluster_sync();   // every block holds its inverse 512-point transform
+                cross_gather<L, CL, CP, TV>(tile, crank, tv, cp, a.twX, [&](unsigned row, float4 v) {
+                    if (valid) st4(axis_dst(a, lbase, pbase, row), v);
+                });
+            }
         }
+        if constexpr (CL > 1) cluster_sync();   // no CTA leaves while a peer may still read its block (doInv is cluster-uniform)
     }
 }
 
 template <int L, int KIND, int SIG>
 __global__ void __launch_bounds__(AxisCfg<L>::THREADS, (AxisCfg<L>::MINB > 2 ? 2 : AxisCfg<L>::MINB))
 axis_kstage_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
+    axis_kstage_body<L, KIND, SIG, void>(a, ks);
+}
+template <int L, int KIND, int SIG>
+__global__ void __cluster_dims__(AxisCfg<L>::CL, 1, 1) __launch_bounds__(AxisCfg<L>::THREADS, (AxisCfg<L>::MINB > 2 ? 2 : AxisCfg<L>::MINB))
+axis_kstage_cluster_kernel(const __grid_constant__ AxisArgs a, const __grid_constant__ KStageD ks) {
     axis_kstage_body<L, KIND, SIG, void>(a, ks);
 }
 

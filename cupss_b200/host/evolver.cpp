@@ -345,13 +345,14 @@ int evolver::advanceTime() {
     return 0;
 }
 
-void evolver::refreshHostMirror(field *f, bool real_part, bool comp_part) {
+void evolver::refreshHostMirror(field *f, bool real_part, bool comp_part, bool keep_exact) {
     if (!plan || f->engine_id < 0) return;
     const size_t slab = (size_t)sx * sy * (sz / partRanks) * partRank;
     // Until the first step after an upload the host real array is the device state bit for bit (the reference's real_array_d is
     // a plain copy of it, src/field_init.cpp; writeOut at step 0 prints the initial condition exactly); the engine only keeps
     // the spectrum, and spectrum -> real would return the same values with 1e-7 of round-off on top.
-    if (real_part && !f->mirror_in_sync) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array + slab)), "download_real");
+    // (Only the output writer asks for this: an explicit copyDeviceToHost always returns the device state.)
+    if (real_part && !(keep_exact && f->mirror_in_sync)) engineCheck(cupss_b200_download_real(plan, f->engine_id, reinterpret_cast<float *>(f->real_array + slab)), "download_real");
     // partitioned: collective (every rank calls it); each rank receives the kz planes of its own z-slab of the full spectrum
     if (comp_part) engineCheck(cupss_b200_download_comp(plan, f->engine_id, reinterpret_cast<float *>(f->comp_array + slab)), "download_comp");
 }

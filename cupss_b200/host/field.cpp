@@ -75,7 +75,7 @@ void field::precalculateImplicit(float) { /* implicit and noise factors are eval
 // (format of /root/reference/src/field.cpp:350-402; NaN aborts with exit(1)).
 void field::writeToFile(int step, int dim, int precision) {
     if (!outputToFile) return;
-    copyRealDeviceToHost();
+    if (system_p) system_p->refreshHostMirror(this, true, false, /*keep_exact=*/true);
     const std::string path = "data/" + name + ".csv." + std::to_string(step);
     FILE *fp = std::fopen(path.c_str(), "w+");
     if (!fp) {

@@ -81,7 +81,7 @@ class evolver {
     cupss_b200_plan *enginePlan() { return plan; }
     void setNoiseSeed(unsigned long long seed) { noiseSeed = seed; seedFixed = true; }
     unsigned long long getNoiseSeed() const { return noiseSeed; }   // valid after prepareProblem (default: time, or a hash shared by all ranks)
-    void refreshHostMirror(field *f, bool real_part, bool comp_part);
+    void refreshHostMirror(field *f, bool real_part, bool comp_part, bool keep_exact = false);
     void uploadHostMirror(field *f);   // host real array -> device state (field::copyHostToDevice)
     void markPlanDirty() { planDirty = true; }
     // Slab partition over `nranks` processes (one GPU each); 3-D only.  Host arrays stay full-size, each

@@ -128,6 +128,15 @@ CASES = {
                       ic=dict(phi=("smooth", (0.4, 0.04))), steps=100, threads=0),
     "ch2d_64x4096": dict(shape=(64, 4096, 1), dt=0.05, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + q^2*(a + k*q^2)*phi= - b*q^2*phi^3"],
                          ic=dict(phi=("smooth", (0.4, 0.04))), steps=100, threads=0),
+    # long strided axes shared by a thread-block cluster (kernels_axis.cuh: AxisCfg<L>::CL = 2 / 4 / 8): y passes and k stage of a
+    # 3-D transform (forward, pruned inverse, fused k stage with its two cross levels), and a generic (run-time compiled) k stage
+    "ch3d_32x1024x8": dict(shape=(32, 1024, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                           ic=dict(phi=("smooth", (0.5, 0.05))), steps=40, threads=0),
+    "ch3d_32x8x2048": dict(shape=(32, 8, 2048), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                           ic=dict(phi=("smooth", (0.5, 0.05))), steps=40, threads=0),
+    "kpz2d_128x2048_det": dict(shape=(128, 2048, 1), dt=0.01, fields=[("h", 1), ("iqxh", 0), ("iqyh", 0)], params=dict(l=0.5),
+                              eqs=["dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2", "iqxh = iqx*h", "iqyh = iqy*h"],
+                              ic=dict(h=("smooth", (1.0, 0.1))), steps=40, threads=0),
     "modelh_256": dict(shape=(256, 256, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                        ic=dict(phi=("smooth", (0.5, 0.025, 1, 4))), steps=100, threads=0,   # 8 x 12 periods: linearly unstable band, gradients O(0.1)
                        # Derived fields built from differences of nearly equal terms (projected velocity, its curl): a plain float32

@@ -66,7 +66,8 @@ def test_reference_unit_tests_operators(built, dim, flavour):
                                   "ch3d_256x16x8", "ch2d_1024x32", "ch2d_2048x32", "ch2d_4096x32", "ch3d_1024x32x8", "burgers1d_2048",
                                   "modelh_32", "kpz3d_32_det", "kpz3d_128x16x16_det", "kpz2d_512x16_mixed_powers", "kpz3d_1024x16x8_det", "kpz2d_256x32_mixed_powers", "ops1d_16", "ops3d_16", "bc_even_inhomogeneous_64", "bc_odd_diffusion_64",
                                   "fcb_lowpass_ch2d_64", "fcb_asym_ch3d_16", "fcb_constraint_kpz2d_32", "fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64",
-                                  "bc_clamp_product_64", "bc_clamp_product_1d_128", "ch2d_1024", "ch2d_64x4096", "modelh_256"])
+                                  "bc_clamp_product_64", "bc_clamp_product_1d_128", "ch2d_1024", "ch2d_64x4096", "modelh_256",
+                                  "ch3d_32x1024x8", "ch3d_32x8x2048", "kpz2d_128x2048_det"])
 def test_parity_with_compiled_reference(built, name):
     case = CASES[name]
     lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F
