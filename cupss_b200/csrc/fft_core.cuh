@@ -157,6 +157,54 @@ struct Dft<2, DIR> {
     }
 };
 
+// ---------------------------------------------------------------- band-limited input: pruned DFT of the x pass (kernels_x3.cu)
+// a * conj(t), rotated by (-i)^ROT -- the four sign patterns of the same two multiplies and two fused multiply-adds
+template <int ROT>
+CUPSS_HD float2 cmul_conj_rot(float2 y, float2 t) {
+    if constexpr (ROT == 0) return make_float2(fmaf(y.y, t.y, y.x * t.x), fmaf(y.y, t.x, -(y.x * t.y)));
+    else if constexpr (ROT == 1) return make_float2(fmaf(y.y, t.x, -(y.x * t.y)), fmaf(-y.y, t.y, -(y.x * t.x)));
+    else if constexpr (ROT == 2) return make_float2(fmaf(-y.y, t.y, -(y.x * t.x)), fmaf(-y.y, t.x, y.x * t.y));
+    else return make_float2(fmaf(-y.y, t.x, y.x * t.y), fmaf(y.y, t.y, y.x * t.x));
+}
+
+// x[q] <- (-i)^q x[q] conj(tw[(q-1) M]) for q >= 1 (M = 2 R0: row stride of the strided level's twiddle table)
+template <int R0, int... Q>
+CUPSS_HD void x3_twiddle_rot(float2 (&x)[R0], const float2* tw, cupss_std::integer_sequence<int, Q...>) {
+    ((x[Q] = Q == 0 ? x[Q] : cmul_conj_rot<Q % 4>(x[Q], tw[(Q > 0 ? Q - 1 : 0) * 2 * R0])), ...);
+}
+
+// Inverse R0-point DFT (exponent +) of a vector whose entries Q .. R0-Q-1 are zero (Q = R0/4): the strided level of the x
+// pass when the input is band-limited to |k| <= sx/4 -- the dealiased field of a cubic term.  With x'[q'] = x[q' - Q] (indices
+// mod R0, q' = 0 .. R0/2-1):  X[p] = (-i)^p Y[p],  Y[2r] = DFT_{R0/2}(x')[r],  Y[2r+1] = DFT_{R0/2}(x'[q'] w^q')[r]  (w = e^{2 pi i / R0}).
+// A full butterfly stage, half of the loads and their mirror-pair bookkeeping disappear.  Returns Y in natural order; the caller
+// folds (-i)^p into the twiddle multiplication that follows (cmul_conj_rot).
+template <int R0>
+struct PrunedDft {
+    static constexpr int Q = R0 / 4, N2 = R0 / 2;
+    template <int I>
+    static CUPSS_HD float2 tw1(float2 v) {   // v * w^I, the constant folded at compile time
+        constexpr float c = (float)cx_cos(2.0 * kPi * I / R0), sn = (float)cx_sin(2.0 * kPi * I / R0);
+        return I == 0 ? v : make_float2(fmaf(-v.y, sn, v.x * c), fmaf(v.x, sn, v.y * c));
+    }
+    template <int... I>
+    static CUPSS_HD void twiddle(float2 (&o)[N2], cupss_std::integer_sequence<int, I...>) {
+        ((o[I] = tw1<I>(o[I])), ...);
+    }
+    // lo = x[0 .. Q-1], hi = x[R0-Q .. R0-1]
+    static CUPSS_HD void run(const float2 (&lo)[Q], const float2 (&hi)[Q], float2 (&y)[R0]) {
+        float2 e[N2], o[N2];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) { e[i] = hi[i]; e[Q + i] = lo[i]; }
+#pragma unroll
+        for (int i = 0; i < N2; ++i) o[i] = e[i];
+        twiddle(o, cupss_std::make_integer_sequence<int, N2>{});
+        Dft<N2, +1>::run(e);
+        Dft<N2, +1>::run(o);
+#pragma unroll
+        for (int r = 0; r < N2; ++r) { y[2 * r] = e[r]; y[2 * r + 1] = o[r]; }
+    }
+};
+
 // ---------------------------------------------------------------- level plan: L -> radices
 template <int L> struct FftLevels;
 #define CUPSS_LEVELS(L_, N_, A_, B_, C_, D_)                                              \

@@ -35,7 +35,8 @@ __device__ __forceinline__ unsigned x3pad(unsigned idx) { return idx + 2u * (idx
 
 // POLY: the real-space stage is c0*r^p0 + c1*r^p1 of the one input (powers up to 4, c1 = 0 for a single monomial) instead of
 // the straight-line c*r^2 / c*r^3 of the headline class.
-template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS, bool POLY = false>
+// PRUNE: the input is known (launcher) to be band-limited to kx <= SX/4; the inverse strided level runs PrunedDft.
+template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS, bool POLY = false, bool PRUNE = false>
 __global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant__ XArgs a) {
     using Cfg = X3Cfg<SX, NT>;
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1, M = Cfg::M, TL = Cfg::TL, LB = Cfg::LB, H = R0 / 2;
@@ -56,7 +57,45 @@ __global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant_
     float2 xA[R0], xB[R0];
 
     // ------------------------------------------------ inverse, strided level: form C from the half-spectrum lines
-    {
+    if constexpr (PRUNE) {
+        constexpr int Q = R0 / 4;   // live: k = j + M q with q < Q, and k = M Q = SX/4 on row 0
+        const float2* pa = a.in[0] + lA * a.pitch;
+        const float2* pb = a.in[0] + lB * a.pitch;
+        auto form = [&](unsigned k, float2& c, float2& m) {   // c = A[k] + i B[k],  m = conj(A[k]) + i conj(B[k]) = C[sx - k]
+            float2 A = hasA ? __ldg(pa + k) : z;
+            float2 B = hasB ? __ldg(pb + k) : z;
+            if (k == 0) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of the self-conjugate bin
+            c = make_float2(A.x - B.y, A.y + B.x);
+            m = make_float2(A.x + B.y, B.x - A.y);
+        };
+        float2 cA[Q], mA[Q], cB[Q], mB[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            form(jA + M * q, cA[q], mA[q]);
+            form(jB + M * q, cB[q], mB[q]);
+        }
+        // k = SX/4 (row 0 only): predicated loads in the same burst as the others, zeros elsewhere
+        float2 ev, od;
+        {
+            const float2 A = (t0 && hasA) ? __ldg(pa + SX / 4) : z;
+            const float2 B = (t0 && hasB) ? __ldg(pb + SX / 4) : z;
+            const float2 c = make_float2(A.x - B.y, A.y + B.x), m = make_float2(A.x + B.y, B.x - A.y);
+            ev = cadd(m, c); od = csub(m, c);   // Y[p] += m + (-1)^p c
+        }
+        // upper ends x[R0-Q .. R0-1] of the two rows: the mirrors (same placement as the general branch below, zeros dropped)
+        float2 hiA[Q], hiB[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) hiB[i] = t0 ? mB[Q - 1 - i] : mA[Q - 1 - i];
+        hiA[0] = t0 ? z : mB[Q - 1];   // row 0: x[R0-Q] is the mirror of k = SX/4, added below
+#pragma unroll
+        for (int i = 1; i < Q; ++i) hiA[i] = t0 ? mA[Q - i] : mB[Q - 1 - i];
+        PrunedDft<R0>::run(cA, hiA, xA);
+        PrunedDft<R0>::run(cB, hiB, xB);
+        if (t0) {   // (two lanes of the warp: the other lanes hold zeros in ev / od)
+#pragma unroll
+            for (int p2 = 0; p2 < R0; p2 += 2) { xA[p2] = cadd(xA[p2], ev); xA[p2 + 1] = cadd(xA[p2 + 1], od); }
+        }
+    } else {
         const float2* pa = a.in[0] + lA * a.pitch;
         const float2* pb = a.in[0] + lB * a.pitch;
         const int kmax = a.kmax[0];
@@ -82,14 +121,19 @@ __global__ void __launch_bounds__(NT, MINB) xpass3_kernel(const __grid_constant_
         xA[H] = t0 ? cMid : mB[H - 1];
 #pragma unroll
         for (int i = 1; i < H; ++i) xA[H + i] = t0 ? mA[H - i] : mB[H - 1 - i];
+        Dft<R0, +1>::run(xA);
+        Dft<R0, +1>::run(xB);
     }
-    Dft<R0, +1>::run(xA);
-    Dft<R0, +1>::run(xB);
     __syncthreads();   // twiddle table complete
+    if constexpr (PRUNE) {   // X[q] = (-i)^q Y[q]: the rotation rides on the twiddle multiplication
+        x3_twiddle_rot(xA, twS + jA, cupss_std::make_integer_sequence<int, R0>{});
+        x3_twiddle_rot(xB, twS + jB, cupss_std::make_integer_sequence<int, R0>{});
+    } else {
 #pragma unroll
-    for (int q = 1; q < R0; ++q) {
-        xA[q] = cmul_conj(xA[q], twS[(q - 1) * M + jA]);
-        xB[q] = cmul_conj(xB[q], twS[(q - 1) * M + jB]);
+        for (int q = 1; q < R0; ++q) {
+            xA[q] = cmul_conj(xA[q], twS[(q - 1) * M + jA]);
+            xB[q] = cmul_conj(xB[q], twS[(q - 1) * M + jB]);
+        }
     }
 #pragma unroll
     for (int q = 0; q < R0; ++q) {
@@ -335,20 +379,20 @@ __global__ void __launch_bounds__(128, 3) xpass3s_kernel(const __grid_constant__
     if (t0) emit(SX / 2, xA[H], xA[H]);
 }
 
-template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS, bool POLY = false>
+template <int SX, int NT, int MINB = X3Cfg<SX, NT>::CTAS, bool POLY = false, bool PRUNE = false>
 static cudaError_t launch_x3_size(XArgs& a, cudaStream_t st) {
     using Cfg = X3Cfg<SX, NT>;
     static bool attr = false;
     if (!attr) {
         if (Cfg::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT, MINB, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(xpass3_kernel<SX, NT, MINB, POLY, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const long long njobs = (a.nlines + 1) / 2;
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
-    xpass3_kernel<SX, NT, MINB, POLY><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    xpass3_kernel<SX, NT, MINB, POLY, PRUNE><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -393,6 +437,11 @@ cudaError_t launch_xpass3(int sx, XArgs& a, cudaStream_t st) {
         return cudaErrorInvalidValue;
     }
     static const int nt = [] { const char* e = getenv("CUPSS_B200_X3_THREADS"); return e ? atoi(e) : 128; }();   // measured (profiles/README.md): 0.202 ms at 128, 0.208 at 64, 0.229 at 256
+    static const bool noPrune = [] { const char* e = getenv("CUPSS_B200_X3_NOPRUNE"); return e && e[0] == '1'; }();
+    // the pruned instantiation fits 96 registers (4 bytes of spills): five 4-warp CTAs per SM, 0.199 -> 0.192 ms (profiles/README.md, r2j)
+    static const int minb = [] { const char* e = getenv("CUPSS_B200_X3_MINB"); return e ? atoi(e) : 5; }();
+    if (sx == 512 && a.kmax[0] == 128 && nt == 128 && !noPrune)   // band-limited to sx/4: pruned strided level
+        return minb == 5 ? launch_x3_size<512, 128, 5, false, true>(a, st) : launch_x3_size<512, 128, 4, false, true>(a, st);
     if (sx == 512) return nt == 256 ? launch_x3_size<512, 256>(a, st) : (nt == 64 ? launch_x3_size<512, 64>(a, st) : launch_x3_size<512, 128>(a, st));
     if (sx == 128) return launch_x3_size<128, 256>(a, st);
     return cudaErrorInvalidValue;

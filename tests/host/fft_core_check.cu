@@ -80,8 +80,46 @@ bool check() {
     return worst < 5e-7;
 }
 
+// PrunedDft<R0> (strided level of the x pass for input band-limited to sx/4) and the rotation folded into the twiddle
+// multiplication: against the full in-register DFT of the zero-padded vector.
+template <int R0>
+bool check_pruned() {
+    constexpr int Q = R0 / 4, M = 2 * R0;
+    float2 lo[Q], hi[Q], full[R0], y[R0];
+    std::vector<float2> tw((R0 - 1) * M);
+    for (int q = 1; q < R0; ++q)
+        for (int j = 0; j < M; ++j) {
+            const double a = -2.0 * kPi * (double)(j * q) / (double)(R0 * M);
+            tw[(q - 1) * M + j] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    double worst = 0;
+    for (int trial = 0; trial < 8; ++trial) {
+        for (int i = 0; i < R0; ++i) full[i] = make_float2(0.0f, 0.0f);
+        for (int i = 0; i < Q; ++i) {
+            lo[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+            hi[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+            full[i] = lo[i]; full[R0 - Q + i] = hi[i];
+        }
+        const int j = trial % M;
+        PrunedDft<R0>::run(lo, hi, y);
+        x3_twiddle_rot(y, tw.data() + j, cupss_std::make_integer_sequence<int, R0>{});
+        Dft<R0, +1>::run(full);
+        for (int q = 1; q < R0; ++q) full[q] = cmul_conj(full[q], tw[(q - 1) * M + j]);
+        double err = 0, nrm = 0;
+        for (int p = 0; p < R0; ++p) {
+            err += (double)(y[p].x - full[p].x) * (y[p].x - full[p].x) + (double)(y[p].y - full[p].y) * (y[p].y - full[p].y);
+            nrm += (double)full[p].x * full[p].x + (double)full[p].y * full[p].y;
+        }
+        worst = std::max(worst, std::sqrt(err / nrm));
+    }
+    printf("PrunedDft<%d> + rotated twiddles vs full DFT: %.3e\n", R0, worst);
+    return worst < 5e-7;
+}
+
 int main() {
     int bad = 0;
+    if (!check_pruned<16>()) bad++;
+    if (!check_pruned<8>()) bad++;
 #define CHK(L) if (!check<L>()) bad++;
     CHK(1) CHK(2) CHK(4) CHK(8) CHK(16) CHK(32) CHK(64) CHK(128) CHK(256) CHK(512) CHK(1024) CHK(2048) CHK(4096) CHK(8192)
     printf(bad ? "FAIL\n" : "OK\n");
