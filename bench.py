@@ -37,7 +37,7 @@ EQ = "dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "       # examples/03_cahn
 PARAMS = (("a", -1.0), ("b", 1.0), ("k", 4.0))
 DT = 0.01
 FALLBACK_HBM = 6650.0   # GB/s, /opt/skills/guides/B200_PROFILING.md
-NVLINK_NOMINAL, NVLINK_MEASURED = 900.0, 770.0   # GB/s per direction per GPU (B200_PROFILING.md: nominal / measured peer copy)
+NVLINK_NOMINAL, NVLINK_MEASURED = 900.0, 706.0   # GB/s per direction per GPU: nominal / peer STORES measured on this pool (tools/ubench/p2p_push.cu, profiles/r2b_p2p_push.txt)
 PARITY_TOL = 1e-5       # BASELINE.json north_star
 GOLDEN_512 = os.path.join(ROOT, "tests", "golden", "ch3d_512_ref.npz")
 MODELH_FIELDS = [("phi", 1), ("iqxphi", 0), ("iqyphi", 0), ("sigxx", 0), ("sigxy", 0), ("vx", 0), ("vy", 0), ("w", 0), ("P", 0)]
@@ -645,7 +645,7 @@ def main():
     nvlink = None
     if world > 1:
         nvlink = {"bytes_per_step_per_gpu": comm, "GBps_per_direction_over_the_whole_step": comm * value / 1e9,
-                  "peak_nominal": NVLINK_NOMINAL, "peak_measured_peer_copy": NVLINK_MEASURED,
+                  "peak_nominal": NVLINK_NOMINAL, "peak_measured_peer_stores": NVLINK_MEASURED,
                   "frac_of_nominal": comm * value / 1e9 / NVLINK_NOMINAL, "frac_of_measured": comm * value / 1e9 / NVLINK_MEASURED,
                   "what": "bytes this rank stores into peers' receive slots per step / step time: the share of the step during which the link would be busy at its peak"}
 

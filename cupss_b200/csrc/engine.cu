@@ -273,6 +273,7 @@ static void prepare_tma(cupss::AxisArgs& a, int L, bool kstage) {
     if (!enc || L < 32 || !a.in || cupss::axis_cluster_size(L) > 1) return;   // cluster kernels load rows inside their cross level
     const int C = cupss::axis_tile_cols(L);
     const long long rpc = (long long)a.ain.rpcMask + 1, nchunk = L / rpc;
+    const bool cyclic = a.ain.locShift > 0;   // row = local * nchunk + chunk: the chunk index runs fastest along the rows
     int B = L < 256 ? L : 256;
     if (!kstage && a.rowCut >= 0) {   // pruned inverse: boxes over [0, cut) and [L - cut, L)
         const int c = a.rowCut;
@@ -284,6 +285,10 @@ static void prepare_tma(cupss::AxisArgs& a, int L, bool kstage) {
     Dim d[3] = {{(unsigned long long)rpc, (unsigned long long)rs * 8ull, (unsigned)(B < rpc ? B : rpc), 0},
                 {(unsigned long long)nchunk, (unsigned long long)cs * 8ull, (unsigned)(B < rpc ? 1 : B / rpc), 1},
                 {(unsigned long long)a.nbatch, (unsigned long long)bs * 8ull, 1u, 2}};
+    if (cyclic) {   // a box of B consecutive rows = min(B, P) chunks x B / that locals, chunk index fastest in shared memory
+        d[1].box = (unsigned)(B < nchunk ? B : nchunk);
+        d[0].box = (unsigned)(B < nchunk ? 1 : B / nchunk);
+    }
     unsigned long long top = 0;
     for (const Dim& x : d) if (x.size > 1) top = std::max(top, x.size * x.stride);
     if (top == 0) top = 128;
@@ -291,7 +296,9 @@ static void prepare_tma(cupss::AxisArgs& a, int L, bool kstage) {
         if (x.size > 1 && (x.stride == 0 || (x.stride & 15ull))) return;
         if (x.size <= 1) { x.size = 1; x.stride = top; top *= 2; }   // degenerate axes: any legal stride, kept monotonic
     }
-    std::stable_sort(d, d + 3, [](const Dim& p, const Dim& q) { return p.stride < q.stride; });
+    if (cyclic) std::swap(d[0], d[1]);   // dimension order = order in the box: chunk, local, batch (strides not monotonic; if the
+                                         // encoder refuses that, the cp.async prologue runs)
+    else std::stable_sort(d, d + 3, [](const Dim& p, const Dim& q) { return p.stride < q.stride; });
     cuuint64_t gdim[4] = {(cuuint64_t)(2 * a.ncol), d[0].size, d[1].size, d[2].size};
     cuuint64_t gstr[3] = {d[0].stride, d[1].stride, d[2].stride};
     cuuint32_t box[4] = {(cuuint32_t)(2 * C), d[0].box, d[1].box, d[2].box};
@@ -366,6 +373,10 @@ struct cupss_b200_plan {
     int dim;
     int rank = 0, nranks = 1;
     int zl, kyl;           // local z planes (real space) / local ky rows (Fourier space)
+    // Fourier space: rank r owns the rows ky = r, r + P, r + 2P, ... (cyclic) so that the |ky| <= cut rows a dealiased inverse
+    // transform keeps -- and sends back -- are spread evenly over the ranks; with contiguous blocks (CUPSS_B200_KY_BLOCK=1) half of
+    // the ranks own none of them at P = 4 and 8 and the others do, and push, twice the share.
+    bool kyCyclic = false;
     int ncol, pitch;
     size_t specElems;      // float2 per spectrum-shaped array on this rank
     int dealiasRule = CUPSS_B200_DEALIAS_GPU_RULE;
@@ -478,7 +489,8 @@ struct cupss_b200_plan {
         a.sx = sx; a.sy = sy; a.sz = sz;
         a.maskOn = 0; a.cutx = a.cuty = a.cutz = 0;
         a.pruneOn = 0; a.pruneCutX = a.pruneCutY = 0; a.rowCut = -1;
-        a.kyBase = rank * kyl;
+        a.kyBase = kyCyclic ? rank : rank * kyl;
+        a.kyStride = kyCyclic ? nranks : 1;
     }
     // last axis of the transform: z in 3-D (rows kz, batch ky_local), y in 2-D, nothing in 1-D
     int make_last_axis(AxisArgs& a, int* L) {
@@ -488,7 +500,7 @@ struct cupss_b200_plan {
         if (dim == 3) { n.bs = pitch; n.rs = (long long)kyl * pitch; a.nbatch = kyl; a.axis = 2; }
         else if (dim == 2) { n.bs = 0; n.rs = pitch; a.nbatch = 1; a.axis = 1; }
         else { n.bs = 0; n.rs = 0; a.nbatch = 1; a.axis = 0; }
-        n.cs = 0; n.rpcShift = ilog2(*L); n.rpcMask = *L - 1;
+        n.cs = 0; n.rpcShift = ilog2(*L); n.rpcMask = *L - 1; n.chunkMask = 0; n.locShift = 0;
         a.ain = n; a.aout = n;
         return get_axis_twiddles(*L, a);
     }
@@ -497,9 +509,11 @@ struct cupss_b200_plan {
         fill_common(a, sy);
         a.nbatch = zl; a.axis = 1;
         AxisAddr nat{}, exc{};
-        nat.bs = (long long)sy * pitch; nat.rs = pitch; nat.cs = 0; nat.rpcShift = ilog2(sy); nat.rpcMask = sy - 1;
+        nat.bs = (long long)sy * pitch; nat.rs = pitch; nat.cs = 0; nat.rpcShift = ilog2(sy); nat.rpcMask = sy - 1; nat.chunkMask = 0; nat.locShift = 0;
         exc.bs = (long long)kyl * pitch; exc.rs = pitch; exc.cs = (long long)zl * kyl * pitch;
-        exc.rpcShift = ilog2(kyl); exc.rpcMask = kyl - 1;
+        exc.rpcMask = kyl - 1; exc.chunkMask = nranks - 1;
+        if (kyCyclic) { exc.rpcShift = 0; exc.locShift = ilog2(nranks); }   // ky = ky_local * P + peer
+        else { exc.rpcShift = ilog2(kyl); exc.locShift = 0; }              // ky = peer * kyl + ky_local
         if (forward) { a.ain = nat; a.aout = exc; } else { a.ain = exc; a.aout = nat; }
         return get_axis_twiddles(sy, a);
     }
@@ -554,8 +568,11 @@ struct cupss_b200_plan {
     // Receive-side addressing of a pushed exchange: slot layout [src rank][z_local][ky_local][pitch].
     void set_push(AxisArgs& a, int slot, bool rowsAreKy) {
         a.pushOn = 1;
-        if (rowsAreKy) { a.pushShift = ilog2(kyl); a.pushMask = kyl - 1; a.pushRs = pitch; a.pushBs = (long long)kyl * pitch; }   // y pass: batch = z_local
-        else { a.pushShift = ilog2(zl); a.pushMask = zl - 1; a.pushRs = (long long)kyl * pitch; a.pushBs = pitch; }               // z pass: batch = ky_local
+        a.pushPeerMask = nranks - 1; a.pushLocShift = 0;
+        if (rowsAreKy) {   // y pass: batch = z_local; the row ky goes to the rank that owns it
+            a.pushMask = kyl - 1; a.pushRs = pitch; a.pushBs = (long long)kyl * pitch;
+            if (kyCyclic) { a.pushShift = 0; a.pushLocShift = ilog2(nranks); } else a.pushShift = ilog2(kyl);
+        } else { a.pushShift = ilog2(zl); a.pushMask = zl - 1; a.pushRs = (long long)kyl * pitch; a.pushBs = pitch; }   // z pass: batch = ky_local, z-slabs are contiguous
         a.pushBase = (long long)kArenaHeader + (long long)slot * (long long)specElems + (long long)rank * zl * kyl * pitch;
         for (int d = 0; d < CUPSS_MAX_PEERS; ++d) a.push[d] = d < nranks ? peerArena[d] : nullptr;
     }
@@ -1228,6 +1245,7 @@ struct cupss_b200_plan {
             }
         }
         float2* invOut = nullptr;
+        double invLive = 1.0;   // share of the fused inverse's output that is not pruned away (written / pushed at all)
         if (ks.hasInv) {
             if (dim == 3) CKR(get_scratch(sc++, &invOut)); else invOut = fields[invField].W2;
         }
@@ -1241,6 +1259,7 @@ struct cupss_b200_plan {
             const double fx = (double)std::min(ncol, (cx / C + 1) * C) / ncol;
             const double fy = dim == 3 ? std::min(1.0, (2.0 * cy + 1.0) / sy) : 1.0;
             k.bytes = (double)(ks.hasFwd + ks.nsrc + ks.nout) * spec_bytes() + fx * fy * spec_bytes();
+            invLive = fx * fy;
         }
         const bool pushInv = nranks > 1 && useP2P && dim == 3;
         std::vector<std::pair<int, float2*>> w1s;   // (field, input of its inverse y pass)
@@ -1248,7 +1267,7 @@ struct cupss_b200_plan {
         if (ks.hasInv && pushInv) {
             const int slot = arenaNext++;
             set_push(k.ax, slot, false);
-            k.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+            k.commBytes = invLive * (double)zl * kyl * pitch * 8.0 * (nranks - 1);   // average over the ranks (exact per rank with the cyclic ky distribution)
             snprintf(k.name, sizeof k.name, "kstage_push_%s", tag);
             if (xPipe) pipeK.push_back(k);
             else { out.push_back(k); add_barrier(out, "xbar_inv"); }
@@ -1269,7 +1288,14 @@ struct cupss_b200_plan {
             if (pushInv) {
                 const int slot = arenaNext++;
                 set_push(z.ax, slot, false);
-                z.commBytes = (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+                {
+                    double live = 1.0;
+                    if (z.ax.pruneOn) {
+                        const int C = axis_tile_cols(z.L);
+                        live = (double)std::min(ncol, (z.ax.pruneCutX / C + 1) * C) / ncol * std::min(1.0, (2.0 * z.ax.pruneCutY + 1.0) / sy);
+                    }
+                    z.commBytes = live * (double)zl * kyl * pitch * 8.0 * (nranks - 1);
+                }
                 snprintf(z.name, sizeof z.name, "lastinv_push_%s", tag);
                 if (xPipe) pipeLI.push_back(z);
                 else { out.push_back(z); add_barrier(out, "xbar_inv"); }
@@ -1446,7 +1472,7 @@ struct cupss_b200_plan {
         Field& F = fields[f];
         if (!F.S) return fail(CUPSS_B200_ERR_STATE, "field %s has no device data", F.name.c_str());
         if (!viewBuf) CK(cudaMalloc(&viewBuf, (size_t)sx * sy * zl * sizeof(float2)));
-        CK(launch_spectrum_expand(F.S, viewBuf, sx, sy, sz, pitch, sy, 0, sz, stream));
+        CK(launch_spectrum_expand(F.S, viewBuf, sx, sy, sz, pitch, sy, 0, sz, 1, stream));
         CK(cudaStreamSynchronize(stream));
         *dev = viewBuf;
         return CUPSS_B200_OK;
@@ -1561,6 +1587,8 @@ int cupss_b200_set_partition(cupss_b200_plan* p, int rank, int nranks, const voi
     if (nranks > CUPSS_MAX_PEERS) return fail(CUPSS_B200_ERR_ARG, "at most %d ranks", CUPSS_MAX_PEERS);
     const char* na = getenv("CUPSS_B200_NCCL_A2A");
     p->useP2P = !(na && na[0] == '1');
+    const char* kb = getenv("CUPSS_B200_KY_BLOCK");
+    p->kyCyclic = !(kb && kb[0] == '1');
     p->zl = p->sz / nranks; p->kyl = p->sy / nranks;
     p->specElems = (size_t)p->pitch * p->kyl * p->sz;   // == pitch * sy * zl
     if (!p->hostErr) {
@@ -1707,7 +1735,7 @@ static int download_comp_impl(cupss_b200_plan* p, int f, float* host) {
         NK(g_nccl.AllGather(F.S, all, p->specElems * 2, /*ncclFloat*/ 7, p->comm, p->stream));
         half = all;
     }
-    CK(launch_spectrum_expand(half, p->viewBuf, p->sx, p->sy, p->sz, p->pitch, p->kyl, p->rank * p->zl, p->zl, p->stream));
+    CK(launch_spectrum_expand(half, p->viewBuf, p->sx, p->sy, p->sz, p->pitch, p->kyl, p->rank * p->zl, p->zl, p->kyCyclic ? p->nranks : 1, p->stream));
     CK(cudaMemcpyAsync(host, p->viewBuf, n * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     if (all) CK(cudaFree(all));

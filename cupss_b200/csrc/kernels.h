@@ -10,12 +10,17 @@ namespace cupss {
 constexpr int CUPSS_MAX_PEERS = 8;
 
 // Addressing of one side (input or output) of a strided-axis pass.  Row r of batch b, column c:
-//   b*bs + (r >> rpcShift)*cs + (r & (rpc-1))*rs + c          (float2 elements)
-// Natural layouts use rpc = L (one chunk).  The multi-GPU exchange layout [peer][z_loc][ky_loc][kx]
-// of the y pass uses rpc = ky_loc count, cs = peer chunk stride.
+//   b*bs + chunk(r)*cs + local(r)*rs + c          (float2 elements)
+//   chunk(r) = (r >> rpcShift) & chunkMask,  local(r) = (r >> locShift) & rpcMask
+// Natural layouts: one chunk (rpcShift = log2 L, locShift = 0, rpcMask = L-1).  The multi-GPU exchange layout
+// [peer][z_loc][ky_loc][kx] of the y pass: chunk = the peer that owns row ky, local = its index there --
+//   block distribution  (ky = peer*kyl + ky_loc):  rpcShift = log2 kyl, locShift = 0
+//   cyclic distribution (ky = ky_loc*P + peer):    rpcShift = 0, chunkMask = P-1, locShift = log2 P
+// (cyclic is the default: the rows a dealiased inverse transform keeps, |ky| <= cut, are then spread evenly over the ranks).
 struct AxisAddr {
     long long bs, cs, rs;
     int rpcShift, rpcMask;
+    int chunkMask, locShift;
 };
 
 struct AxisArgs {
@@ -29,7 +34,7 @@ struct AxisArgs {
     const float2* tw;    // level twiddle table of the transform a CTA runs (fft_core.cuh; 512 points when a cluster shares the axis)
     const float2* twX;   // cluster kernels: (CL-1) x 512 twiddles of the level that couples the CTAs' blocks, else null
     int axis;        // k index carried by the rows: 1 = ky, 2 = kz, 0 = none (L = 1)
-    int kyBase;      // axis == 2: iky = kyBase + batch
+    int kyBase, kyStride;   // axis == 2: iky = kyBase + batch * kyStride (block: rank*kyl, 1; cyclic: rank, P)
     int maskOn, cutx, cuty, cutz;   // plain inverse: dealias mask applied on load
     int sx, sy, sz;
     // Dealias-aware pruning of inverse transforms: a dealiased spectrum is zero outside |n_a| <= cut_a, so
@@ -39,8 +44,10 @@ struct AxisArgs {
     int pruneOn, pruneCutX, pruneCutY;
     int rowCut;
     // Fused slab exchange (multi-GPU): instead of `out`, row r of batch b is stored straight into the receive
-    // buffer of peer (r >> pushShift) over NVLink:  push[peer] + pushBase + b*pushBs + (r & pushMask)*pushRs + col.
+    // buffer of the peer that owns it over NVLink:  push[peer(r)] + pushBase + b*pushBs + loc(r)*pushRs + col,
+    // peer(r) = (r >> pushShift) & pushPeerMask, loc(r) = (r >> pushLocShift) & pushMask (same two distributions as AxisAddr).
     int pushOn, pushShift, pushMask;
+    int pushPeerMask, pushLocShift;
     long long pushRs, pushBs, pushBase;
     float2* push[CUPSS_MAX_PEERS];   // base of every rank's exchange arena (header: flags / epochs / error word)
     int rank, nranks;
@@ -110,7 +117,8 @@ cudaError_t launch_real_expand(const float* in, float2* out, size_t n, cudaStrea
 cudaError_t launch_real_compress(const float2* in, float* out, size_t n, cudaStream_t st);
 // Hermitian half spectrum -> planes [z0, z0 + zl) of the full spectrum float2[sz][sy][sx] (comp_array layout of the reference).
 // `half` is [src][sz][kyl][pitch] with src = ky / kyl: one rank's array when kyl == sy, the all-gathered ky-slabs otherwise.
-cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, cudaStream_t st);
+// cyclicP > 1: the ky rows are dealt out cyclically over cyclicP ranks (src = ky % cyclicP, row ky / cyclicP of its slab).
+cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, int cyclicP, cudaStream_t st);
 cudaError_t launch_xgpu_barrier(const XBarrier& b, cudaStream_t st);
 int axis_tile_cols(int L);          // C used for length L
 // Launch geometry of the k-stage kernel for length L (for kernels compiled at run time)

@@ -230,10 +230,10 @@ __global__ void real_expand_kernel(const float* __restrict__ in, float2* __restr
 __global__ void real_compress_kernel(const float2* __restrict__ in, float* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i].x;
 }
-__global__ void spectrum_expand_kernel(const float2* __restrict__ half, float2* __restrict__ full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl) {
+__global__ void spectrum_expand_kernel(const float2* __restrict__ half, float2* __restrict__ full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, int cyclicP) {
     const size_t n = (size_t)sx * sy * zl;
-    auto at = [&](int k, int j, int i) -> float2 {   // [src = j / kyl][k][j % kyl][i]
-        const int src = j / kyl, jl = j - src * kyl;
+    auto at = [&](int k, int j, int i) -> float2 {   // [src][k][jl][i]: block distribution src = j / kyl, cyclic src = j % P
+        const int src = cyclicP > 1 ? j % cyclicP : j / kyl, jl = cyclicP > 1 ? j / cyclicP : j - src * kyl;
         return half[(((size_t)src * sz + k) * kyl + jl) * pitch + i];
     };
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
@@ -250,8 +250,8 @@ __global__ void spectrum_expand_kernel(const float2* __restrict__ half, float2* 
         full[o] = v;
     }
 }
-cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, cudaStream_t st) {
-    spectrum_expand_kernel<<<148 * 8, 256, 0, st>>>(half, full, sx, sy, sz, pitch, kyl, z0, zl);
+cudaError_t launch_spectrum_expand(const float2* half, float2* full, int sx, int sy, int sz, int pitch, int kyl, int z0, int zl, int cyclicP, cudaStream_t st) {
+    spectrum_expand_kernel<<<148 * 8, 256, 0, st>>>(half, full, sx, sy, sz, pitch, kyl, z0, zl, cyclicP);
     return cudaGetLastError();
 }
 // Hermitian part of a full spectrum, stored as the half spectrum: H(k) = (F(k) + conj F(-k)) / 2 for kx <= sx/2.

@@ -28,18 +28,18 @@ template <int L> struct AxisCfg {
 
 // Element offset of (batch b, row, column col).  32-bit arithmetic: the engine refuses arrays of 2^31 elements or more.
 __device__ __forceinline__ unsigned axis_off(const AxisAddr& a, unsigned b, unsigned row, unsigned col) {
-    return b * (unsigned)a.bs + (row >> a.rpcShift) * (unsigned)a.cs + (row & (unsigned)a.rpcMask) * (unsigned)a.rs + col;
+    return b * (unsigned)a.bs + ((row >> a.rpcShift) & (unsigned)a.chunkMask) * (unsigned)a.cs + ((row >> a.locShift) & (unsigned)a.rpcMask) * (unsigned)a.rs + col;
 }
 // Same with the row-independent part (b * bs + col) hoisted by the caller.
 __device__ __forceinline__ unsigned row_off(const AxisAddr& a, unsigned row) {
-    return (row >> a.rpcShift) * (unsigned)a.cs + (row & (unsigned)a.rpcMask) * (unsigned)a.rs;
+    return ((row >> a.rpcShift) & (unsigned)a.chunkMask) * (unsigned)a.cs + ((row >> a.locShift) & (unsigned)a.rpcMask) * (unsigned)a.rs;
 }
 
 // Destination of row `row`: local array, or the receive buffer of the peer that owns the row (fused slab exchange).
 // `lbase` = out + b*bs + col (local), `pbase` = pushBase + b*pushBs + col (element offset inside every peer's arena).
 __device__ __forceinline__ float2* axis_dst(const AxisArgs& a, float2* lbase, unsigned long long pbase, unsigned row) {
     if (a.pushOn)
-        return a.push[row >> a.pushShift] + pbase + (unsigned long long)((row & (unsigned)a.pushMask)) * (unsigned long long)a.pushRs;
+        return a.push[(row >> a.pushShift) & (unsigned)a.pushPeerMask] + pbase + (unsigned long long)(((row >> a.pushLocShift) & (unsigned)a.pushMask)) * (unsigned long long)a.pushRs;
     return lbase + row_off(a.aout, row);
 }
 
@@ -109,7 +109,7 @@ __device__ __forceinline__ void tile_fetch_tma(float4* tile, float2* twS, unsign
         for (unsigned i = 0; i < nbox; ++i) {
             // pruned: boxes over [0, keepLo) and [keepHi, L)
             const unsigned r0 = pruned ? (i < nbox / 2 ? i * B : keepHi + (i - nbox / 2) * B) : i * B;
-            const int v0 = (int)(r0 & (unsigned)a.ain.rpcMask), v1 = (int)(r0 >> a.ain.rpcShift), v2 = (int)b;
+            const int v0 = (int)((r0 >> a.ain.locShift) & (unsigned)a.ain.rpcMask), v1 = (int)((r0 >> a.ain.rpcShift) & (unsigned)a.ain.chunkMask), v2 = (int)b;
             auto pick = [&](int role) { return role == 0 ? v0 : (role == 1 ? v1 : v2); };
             tma_load_4d(tile + (size_t)r0 * CP, a.tmap, (int)(ct * C * 2), pick(a.tmaSlot[0]), pick(a.tmaSlot[1]), pick(a.tmaSlot[2]), bar);
         }
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     const bool valid = col < (unsigned)a.ncol;
 
     if (a.pruneOn) {   // CTA-uniform: the whole tile is outside the dealias cut-off -> output stays zero
-        const int iyT = a.kyBase + (int)b;
+        const int iyT = a.kyBase + (int)b * a.kyStride;
         const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
         if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
     }
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(AxisCfg<L>::THREADS, AxisCfg<L>::MINB) axis_pl
     };
     auto masked = [&](float4 t, unsigned row) -> float4 {
         if constexpr (MASK) {
-            const int iy = a.axis == 2 ? a.kyBase + (int)b : (a.axis == 1 ? (int)row : 0);
+            const int iy = a.axis == 2 ? a.kyBase + (int)b * a.kyStride : (a.axis == 1 ? (int)row : 0);
             const int iz = a.axis == 2 ? (int)row : 0;
             if (!dealias_keep((int)col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.x = 0.0f; t.y = 0.0f; }
             if (!dealias_keep((int)col + 1, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.z = 0.0f; t.w = 0.0f; }
@@ -375,7 +375,7 @@ axis_plain_cluster_kernel(const __grid_constant__ AxisArgs a) {
     const bool valid = col < (unsigned)a.ncol;
 
     if (a.pruneOn) {   // cluster-uniform: the whole tile is outside the dealias cut-off -> output stays zero
-        const int iyT = a.kyBase + (int)b;
+        const int iyT = a.kyBase + (int)b * a.kyStride;
         const int nyT = iyT > a.sy / 2 ? a.sy - iyT : iyT;
         if ((int)(ct * C) > a.pruneCutX || (a.axis == 2 && nyT > a.pruneCutY)) return;
     }
@@ -387,7 +387,7 @@ axis_plain_cluster_kernel(const __grid_constant__ AxisArgs a) {
         if (!(valid && (row <= keepLo || row >= keepHi))) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         float4 t = ld4(ibase + row_off(a.ain, row));
         if constexpr (MASK) {
-            const int iy = a.axis == 2 ? a.kyBase + (int)b : (a.axis == 1 ? (int)row : 0);
+            const int iy = a.axis == 2 ? a.kyBase + (int)b * a.kyStride : (a.axis == 1 ? (int)row : 0);
             const int iz = a.axis == 2 ? (int)row : 0;
             if (!dealias_keep((int)col, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.x = 0.0f; t.y = 0.0f; }
             if (!dealias_keep((int)col + 1, iy, iz, a.sx, a.sy, a.sz, a.cutx, a.cuty, a.cutz)) { t.z = 0.0f; t.w = 0.0f; }
@@ -433,7 +433,7 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     const bool valid = col < (unsigned)a.ncol, valid1 = col + 1 < (unsigned)a.ncol;
 
     // fixed (per thread) part of the mode index: columns = kx, and ky for a z pass
-    const int iyFix = a.axis == 2 ? a.kyBase + (int)b : 0;
+    const int iyFix = a.axis == 2 ? a.kyBase + (int)b * a.kyStride : 0;
     bool doInv = ks.hasInv != 0;
     if (doInv && a.pruneOn) {   // CTA-uniform: every mode of this tile is masked out -> nothing to transform or store
         const int nyT = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;

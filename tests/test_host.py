@@ -263,21 +263,22 @@ def _slab_worker(rank, world, port, q):
     full = rng.standard_normal((sz, sy, sx))
     mine = full[rank * zl:(rank + 1) * zl]
     xy = np.fft.fft(np.fft.rfft(mine, axis=2), axis=1)                     # x pass then y pass on the z-slab
-    # forward exchange layout written by the y pass: [peer][z_local][ky_local][kx]  (engine.cu make_y_axis)
-    send = np.ascontiguousarray(xy.reshape(zl, world, kyl, ncol).transpose(1, 0, 2, 3))
+    # forward exchange layout written by the y pass: [peer][z_local][ky_local][kx]  (engine.cu make_y_axis); the ky rows are dealt
+    # out cyclically, ky = ky_local * P + peer, so that the low-|ky| rows a dealiased inverse keeps are spread over the ranks
+    send = np.ascontiguousarray(xy.reshape(zl, kyl, world, ncol).transpose(2, 0, 1, 3))
     recv = np.empty_like(send)
     t_send, t_recv = torch.from_numpy(send.view(np.float64).copy()), torch.from_numpy(recv.view(np.float64).copy())
     dist.all_to_all_single(t_recv, t_send)
     got = t_recv.numpy().view(np.complex128).reshape(world * zl, kyl, ncol)   # == natural [sz][ky_local][kx]
     spec = np.fft.fft(got, axis=0)                                           # z pass
-    want = np.fft.rfftn(full)[:, rank * kyl:(rank + 1) * kyl, :]
+    want = np.fft.rfftn(full)[:, rank::world, :]
     err = float(np.max(np.abs(spec - want)))
-    # inverse direction: z-major chunks are contiguous; receiver reads [peer][z_local][ky_local][kx] as ky = peer*kyl+ky_local
+    # inverse direction: z-major chunks are contiguous; receiver reads [peer][z_local][ky_local][kx] as ky = ky_local*P + peer
     back = np.fft.ifft(spec, axis=0)
     t_send = torch.from_numpy(np.ascontiguousarray(back).view(np.float64).copy())
     t_recv = torch.empty_like(t_send)
     dist.all_to_all_single(t_recv, t_send)
-    r = t_recv.numpy().view(np.complex128).reshape(world, zl, kyl, ncol).transpose(1, 0, 2, 3).reshape(zl, sy, ncol)
+    r = t_recv.numpy().view(np.complex128).reshape(world, zl, kyl, ncol).transpose(1, 2, 0, 3).reshape(zl, sy, ncol)
     real = np.fft.irfft(np.fft.ifft(r, axis=1), n=sx, axis=2)
     err2 = float(np.max(np.abs(real - mine)))
     q.put((rank, err, err2))
@@ -286,7 +287,7 @@ def _slab_worker(rank, world, port, q):
 
 def test_slab_exchange_layout_two_ranks_gloo():
     """world_size-2 CPU rendition of the multi-GPU path: z-slabs in real space, ky-slabs in Fourier space, one
-    all-to-all per 3-D transform in the [peer][z_local][ky_local][kx] layout the y-pass kernels address."""
+    all-to-all per 3-D transform in the [peer][z_local][ky_local][kx] layout the y-pass kernels address (cyclic ky ownership)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
