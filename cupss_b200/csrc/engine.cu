@@ -827,6 +827,13 @@ struct cupss_b200_plan {
         }
         z.ax.in = fields[f].S;
         z.bytes = 2.0 * spec_bytes();
+        if (prune) {   // live column tiles x live ky rows (whole tiles skipped); of a live tile only the rows up to the cut-off are read
+            const int C = axis_tile_cols(z.L);
+            const double fx = (double)std::min(ncol, (cx / C + 1) * C) / ncol;
+            const double fy = dim == 3 ? std::min(1.0, (2.0 * cy + 1.0) / sy) : 1.0;
+            const double fr = z.ax.rowCut >= 0 ? std::min(1.0, (2.0 * z.ax.rowCut + 1.0) / z.L) : 1.0;
+            z.bytes = fx * fy * (fr + 1.0) * spec_bytes();
+        }
         return CUPSS_B200_OK;
     }
     // Inverse y pass (3-D) of the dealiased copy of field f into its W2, pruned to the dealias cut-off.

@@ -130,6 +130,9 @@ CASES = {
                          ic=dict(phi=("smooth", (0.4, 0.04))), steps=100, threads=0),
     # long strided axes shared by a thread-block cluster (kernels_axis.cuh: AxisCfg<L>::CL = 2 / 4 / 8): y passes and k stage of a
     # 3-D transform (forward, pruned inverse, fused k stage with its two cross levels), and a generic (run-time compiled) k stage
+    # y and z axes long enough for the TMA prologue incl. the pruned inverse (cut-off 16 rows = one box per end)
+    "ch3d_32x64x64": dict(shape=(32, 64, 64), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
+                          ic=dict(phi=("smooth", (0.5, 0.05))), steps=40, threads=0),
     "ch3d_32x1024x8": dict(shape=(32, 1024, 8), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],
                            ic=dict(phi=("smooth", (0.5, 0.05))), steps=40, threads=0),
     "ch3d_32x8x2048": dict(shape=(32, 8, 2048), dt=0.01, fields=[("phi", 1)], params=CH_PARAMS, eqs=["dt phi + ( a *q^2 + k*q^4)*phi= - b* q^2* phi^3 "],

@@ -47,8 +47,14 @@ def main():
     bc3d = dict(shape=(32, 32, 16), dt=0.002, fields=[("v", 1), ("iqxv", 0), ("x", 0)], params={},
                 eqs=["dt v +0.5*q^2*v = iqx*x*iqxv + x*iqy^2*v", "iqxv = iqx*v"],
                 ic=dict(v=("smooth", (0.6, 0.05)), x=("smooth", (0.3, 0.0))), steps=12, callbacks=[("v", False), ("x", False)], device=0)
+    # long axes shared by thread-block clusters, with the fused push exchange: 1024-row y passes (pushed forward pass, pruned
+    # inverse from the exchange layout) and a 1024-row z axis (k stage whose cross-level gather pushes the rows to their owners)
+    ch_long_y = dict(cases.CASES["ch3d_64x32x16"]); ch_long_y["shape"] = (32, 1024, 16)
+    ch_long_z = dict(cases.CASES["ch3d_64x32x16"]); ch_long_z["shape"] = (32, 16, 1024)
+    kpz_long_z = dict(cases.CASES["kpz3d_32_det"]); kpz_long_z["shape"] = (32, 16, 1024)
     for name, case, steps in (("ch3d_64x32x16", cases.CASES["ch3d_64x32x16"], 20), ("kpz3d_32_det", cases.CASES["kpz3d_32_det"], 10),
-                              ("ops3d_16", cases.CASES["ops3d_16"], 3), ("bc3d_mirror_callbacks", bc3d, 12)):
+                              ("ops3d_16", cases.CASES["ops3d_16"], 3), ("bc3d_mirror_callbacks", bc3d, 12),
+                              ("ch3d_32x1024x16", ch_long_y, 8), ("ch3d_32x16x1024", ch_long_z, 8), ("kpz3d_32x16x1024", kpz_long_z, 6)):
         sx, sy, sz = case["shape"]
         dev = case.get("device", 1)
         ev = cases.build_system(case, device=dev)

@@ -67,7 +67,7 @@ def test_reference_unit_tests_operators(built, dim, flavour):
                                   "modelh_32", "kpz3d_32_det", "kpz3d_128x16x16_det", "kpz2d_512x16_mixed_powers", "kpz3d_1024x16x8_det", "kpz2d_256x32_mixed_powers", "ops1d_16", "ops3d_16", "bc_even_inhomogeneous_64", "bc_odd_diffusion_64",
                                   "fcb_lowpass_ch2d_64", "fcb_asym_ch3d_16", "fcb_constraint_kpz2d_32", "fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64",
                                   "bc_clamp_product_64", "bc_clamp_product_1d_128", "ch2d_1024", "ch2d_64x4096", "modelh_256",
-                                  "ch3d_32x1024x8", "ch3d_32x8x2048", "kpz2d_128x2048_det"])
+                                  "ch3d_32x1024x8", "ch3d_32x8x2048", "kpz2d_128x2048_det", "ch3d_32x64x64"])
 def test_parity_with_compiled_reference(built, name):
     case = CASES[name]
     lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F
@@ -507,6 +507,41 @@ def test_output_files_match_the_reference_byte_for_byte(built, tmp_path, shape):
         assert same >= 0.90 * (len(w) - 1), (name, same, len(w) - 1)
         if step > steps:
             assert same >= 0.995 * (len(w) - 1), (name, same, len(w) - 1)
+
+
+_VARIANT_CODE = ("import sys, os; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+                 "import numpy as np, cases\n"
+                 "out = cases.run_case(cases.CASES[sys.argv[1]])\n"
+                 "np.savez(sys.argv[2], **out)\n") % (ROOT, os.path.join(ROOT, "tests"))
+
+
+def _run_variant(name, env, path):
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_CODE, name, path], env=e, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return dict(np.load(path))
+
+
+@pytest.mark.parametrize("name,env,bitwise", [
+    ("ch3d_32x64x64", {"CUPSS_B200_TMA": "0"}, True),             # TMA box loads vs per-thread cp.async: the same tile, the same arithmetic
+    ("ch3d_64x32x16", {"CUPSS_B200_TMA": "0"}, True),
+    ("modelh_32", {"CUPSS_B200_TMA": "0"}, True),
+    ("ch3d_64x32x16", {"CUPSS_B200_ZCHUNK": "4"}, True),           # z-chunked x -> forward-y pipeline on two lanes
+    ("ch3d_64x32x16", {"CUPSS_B200_ZCHUNK": "8", "CUPSS_B200_ZCHUNK_LANES": "1"}, True),
+    ("kpz3d_32_det", {"CUPSS_B200_ZCHUNK": "8"}, True),
+    ("ch3d_512x8x8", {"CUPSS_B200_X3_NOPRUNE": "1"}, False),      # pruned strided level of the x pass: other rounding, same transform
+    ("ch3d_512x8x8", {"CUPSS_B200_NO_GRAPH": "1"}, True),
+])
+def test_environment_variants_agree_with_the_default_path(built, tmp_path, name, env, bitwise):
+    """The switchable code paths (README.md: environment switches) produce the default path's result: bit for bit where the
+    arithmetic is the same (other prologue, other launch structure), to 1e-6 where only the rounding differs."""
+    base = _run_variant(name, {}, str(tmp_path / "base.npz"))
+    var = _run_variant(name, env, str(tmp_path / "var.npz"))
+    for f in base:
+        if bitwise:
+            assert np.array_equal(base[f], var[f]), (f, rel_l2(var[f], base[f]))
+        else:
+            assert rel_l2(var[f], base[f]) < 1e-6, (f, rel_l2(var[f], base[f]))
 
 
 def test_copy_host_to_device_uploads_the_edited_array(built):
