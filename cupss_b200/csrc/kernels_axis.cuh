@@ -461,11 +461,17 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
         else if (ks.hasFwd) tile_fetch<L, CP, TV>(tile, tv, cp, valid, ibase, a.ain, [](unsigned p) { return p; }, [](unsigned) { return true; });
     }
     if (CL == 1 && !tma) tw_fetch<S, Cfg::THREADS>(twS, a.tw);
-    if (KIND == KS_SCALAR_Q2 && ks.hasFwd) {
-        // pull this tile's rows of the state spectrum towards L2 while the forward transform runs
-        const float2* p0 = ks.src[0] + (b * (unsigned)a.aout.bs + ct * C);
-        for (unsigned r = threadIdx.x; r < (unsigned)S; r += Cfg::THREADS)   // the rows this CTA's block will hold: crank + CL r
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (crank + (unsigned)CL * r) * krs));
+    if (ks.hasFwd) {
+        // pull this tile's rows of the state spectrum (generic sweeps: of every pointwise source) towards L2 while the forward
+        // transform runs: the generic evaluator reads its sources mode by mode inside a rolled loop, one exposed latency per row
+        // (noisy KPZ-3D 512^3 k stage 0.807 -> 0.769 ms).  Without a forward transform there is nothing to hide the prefetch
+        // behind and issuing it for the whole tile at once costs more than it saves (KPZ constraint sweep 0.775 -> 0.927 ms).
+        const int nsrc = KIND == KS_SCALAR_Q2 ? 1 : ks.nsrc;
+        for (int sI = 0; sI < nsrc; ++sI) {
+            const float2* p0 = ks.src[sI] + (b * (unsigned)a.aout.bs + ct * C);
+            for (unsigned r = threadIdx.x; r < (unsigned)S; r += Cfg::THREADS)   // the rows this CTA's block will hold: crank + CL r
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (crank + (unsigned)CL * r) * krs));
+        }
     }
     if (tma) {
         tile_wait_tma(bar);
