@@ -405,6 +405,7 @@ struct cupss_b200_plan {
     int zChunk = 0;        // planes per chunk of the x -> forward-y pipeline (0: off)
     int zChunkLanes = 2;
     int xChunks = 1;       // column chunks of the slab-exchange pipeline (1: off, launches run one after the other)
+    bool laneFanout = true;   // 1-D / 2-D grids: independent launches of a sweep side by side on the lanes (emit_concurrent)
     // Peer-memory exchange arena (multi-GPU): [header: flags, epochs, error][slot 0][slot 1]...; every rank maps
     // every peer's arena through CUDA IPC, and the y / z pass kernels store their output rows straight into the
     // owner's slot over NVLink (no NCCL, no staging copy on the hot path).
@@ -771,6 +772,13 @@ struct cupss_b200_plan {
     // ------------------------------------------------------------ schedule construction
     struct Mono { float coef; std::vector<int> fac; };
     struct Group { int field; int firstTerm; std::vector<Pres> pres; std::vector<Mono> monos; };
+    static std::vector<int> group_inputs(const Group& g) {   // distinct fields its monomials read
+        std::vector<int> ins;
+        for (const Mono& m : g.monos)
+            for (int fid : m.fac)
+                if (std::find(ins.begin(), ins.end(), fid) == ins.end()) ins.push_back(fid);
+        return ins;
+    }
 
     static bool proportional(const std::vector<Pres>& a, const std::vector<Pres>& b, float* lambda) {
         if (a.size() != b.size()) return false;
@@ -971,6 +979,24 @@ struct cupss_b200_plan {
         for (size_t i = first; i < out.size(); ++i) out[i].pipe = pid;
     }
 
+    // Independent launches of one sweep that do not fill the GPU on their own (2-D grids: a strided-axis pass has ncol / 16
+    // column tiles and no batch dimension -- 65 clusters at 2048^2, 22 when pruned) go out side by side on the lanes and are
+    // joined before the next launch.  Lanes 1, 2 first: a lane forks from everything queued on the main stream so far.
+    void emit_concurrent(std::vector<Launch>& out, std::vector<Launch> v) {
+        if (v.empty()) return;
+        if (v.size() == 1 || dim == 3 || nranks > 1 || !laneFanout) { for (Launch& l : v) out.push_back(l); return; }
+        const int gid = nextGroup++, pid = nextPipe++;
+        double bytes = 0;
+        for (const Launch& l : v) bytes += l.bytes;
+        for (size_t i = 0; i < v.size(); ++i) {
+            Launch& l = v[i];
+            l.lane = (int)((i + 1) % kMaxLanes);
+            l.group = gid; l.pipe = pid;
+            if (i == 0) { snprintf(l.groupName, sizeof l.groupName, "%s", l.name); l.groupBytes = bytes; }
+            out.push_back(l);
+        }
+    }
+
     int build_stage(bool dyn, std::vector<Launch>& out) {
         std::vector<int> outs;
         for (size_t f = 0; f < fields.size(); ++f) if (fields[f].dynamic == dyn) outs.push_back((int)f);
@@ -1022,6 +1048,10 @@ struct cupss_b200_plan {
                     }
                 }
                 if (g1 > g0 && (trial.size() > maxIn || monos > XP_MAX_MONO || g1 - g0 >= (size_t)XP_MAX_OUT)) break;
+                // Long lines: every stashed input costs a line of shared memory (fewer CTAs per SM), so a group joins a launch
+                // only when it shares an input with it -- Model H: phi^3 keeps the single-input kernel, vx*iqxphi + vy*iqyphi
+                // gets a launch of its own.  The results do not depend on the grouping.
+                if (g1 > g0 && xstash1_supported(sx) && trial.size() == ins.size() + group_inputs(groups[g1]).size()) break;
                 if (trial.size() > maxIn || monos > XP_MAX_MONO) return fail(CUPSS_B200_ERR_ARG, "a single term group needs too many fields/monomials for sx = %d (at most %zu fields)", sx, maxIn);
                 ins = trial; nMono = monos; ++g1;
             }
@@ -1072,7 +1102,7 @@ struct cupss_b200_plan {
         // Single GPU, 3-D: the x passes and the forward y passes both work plane by plane, so they run as a z-chunked software
         // pipeline on two streams (emit_xy_pipeline); otherwise the x passes go out whole, right here.
         const bool xyPipe = dim == 3 && nranks == 1 && zChunk > 0 && zl >= 2 * zChunk && zl % zChunk == 0 && !groups.empty();
-        if (!xyPipe) for (Launch& x : xs) out.push_back(x);
+        if (!xyPipe) emit_concurrent(out, xs);
         std::vector<Launch> ys;
         // Slab-partitioned run with the fused push exchange: the exchange side of the sweep is collected per kind and emitted as
         // a column-chunked pipeline over three lanes (emit_exchange_pipeline) instead of one launch after the other.
@@ -1144,6 +1174,7 @@ struct cupss_b200_plan {
         };
         // groups beyond the first get their own last-axis forward pass into a spectrum that the k stage reads pointwise
         std::vector<int> srcOfGroup(groups.size(), -1);
+        std::vector<Launch> lastFwds;
         for (size_t g = 1; g < groups.size(); ++g) {
             Launch z{};
             z.kind = Launch::AXIS_PLAIN; z.dir = -1;
@@ -1153,11 +1184,12 @@ struct cupss_b200_plan {
             CKR(get_scratch(sc++, &that));
             z.ax.in = groupSpec[g]; z.ax.out = that;
             z.bytes = 2.0 * spec_bytes();
-            if (xPipe) pipeLF.push_back(z); else out.push_back(z);
+            if (xPipe) pipeLF.push_back(z); else lastFwds.push_back(z);
             if (ks.nsrc >= KS_MAX_SRC) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
             ks.src[ks.nsrc] = that;
             srcOfGroup[g] = ks.nsrc++;
         }
+        emit_concurrent(out, lastFwds);
 
         int nterm = 0, npres = 0;
         int invField = -1;
@@ -1286,6 +1318,7 @@ struct cupss_b200_plan {
         }
 
         // ---- remaining inverse transforms of dealiased fields
+        std::vector<Launch> lastInvs;
         for (int f : extraInv) {
             Launch z;
             CKR(lastinv_launch(f, tag, z));
@@ -1310,9 +1343,10 @@ struct cupss_b200_plan {
                 pushed.push_back(1);
                 continue;
             }
-            out.push_back(z);
+            lastInvs.push_back(z);
             if (dim == 3) { w1s.push_back({f, w1}); pushed.push_back(0); }
         }
+        emit_concurrent(out, lastInvs);
         for (size_t wi = 0; wi < w1s.size(); ++wi) {
             auto& pr = w1s[wi];
             const float2* yin = pr.second;
@@ -1538,6 +1572,7 @@ int cupss_b200_create(cupss_b200_plan** out, int sx, int sy, int sz, float dx, f
     if (const char* zc = getenv("CUPSS_B200_ZCHUNK")) p->zChunk = atoi(zc);
     if (const char* zl = getenv("CUPSS_B200_ZCHUNK_LANES")) p->zChunkLanes = atoi(zl);
     if (const char* xc = getenv("CUPSS_B200_XCHUNKS")) p->xChunks = std::max(1, atoi(xc));
+    if (getenv("CUPSS_B200_NO_FANOUT")) p->laneFanout = false;
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));

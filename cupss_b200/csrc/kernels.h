@@ -141,6 +141,10 @@ bool xpass4_supported(int sx);
 int host_x4_twiddles(int sx, float2* out);
 cudaError_t launch_xpass4(int sx, XArgs& a, cudaStream_t st);
 cudaError_t launch_xpass4_sumpow(int sx, XArgs& a, cudaStream_t st);
+// one-job stash x pass for long lines (kernels_xs.cu; sx = 1024, 2048, 4096): reached through launch_xpass
+bool xstash1_supported(int sx);
+int xstash1_max_inputs(int sx);
+cudaError_t launch_xstash1(int sx, XArgs& a, cudaStream_t st);
 bool fft_size_supported(int n);
 
 #endif

@@ -399,12 +399,14 @@ static cudaError_t launch_x_mode(int mode, XArgs& a, cudaStream_t st) {
     }
     if (fast && a.nIn > 1) return launch_x<SX, X_HOT, true, true>(a, st);
     if (fast) return launch_x<SX, X_HOT, true>(a, st);
+    if (xstash1_supported(SX)) return launch_xstash1(SX, a, st);   // long lines: one job per CTA (kernels_xs.cu)
     return launch_x<SX, X_HOT, false>(a, st);
 }
 
 // Most inputs one x-pass launch can take for this line length: the real fields of all inputs of a slot are stashed in
 // shared memory next to the line buffer (one slot must fit in 200 KB).
 int xpass_max_inputs(int sx) {
+    if (xstash1_supported(sx)) return xstash1_max_inputs(sx);
     const long long xb = (long long)sx + sx / 8 + 1;   // XCfg<SX>::XB
     const long long fit = (200ll * 1024 - ((long long)sx * 8)) / (xb * (long long)sizeof(float4)) - 1;
     return (int)(fit < 1 ? 1 : (fit > XP_MAX_IN ? XP_MAX_IN : fit));

@@ -16,14 +16,15 @@ def smooth_ic(sx, sy, sz, amp=0.5, noise=0.05, seed=1, kmult=1):
     """O(amp) smooth structure + white noise: exercises the nonlinear terms without sitting on the float32 floor
     (SURVEY.md Appendix C).  kmult scales the wavenumbers of the structure: on a large grid the gradients of a 2-period
     pattern are tiny and DERIVED fields (iqx*phi, stresses, velocities of Model H) would be compared at their own
-    float32 round-off floor instead of at their natural scale."""
+    float32 round-off floor instead of at their natural scale.  A tuple gives one factor per axis (anisotropic grids)."""
     rng = np.random.default_rng(seed)
     z, y, x = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
-    f = amp * np.sin(2 * np.pi * (2 * kmult) * x / sx)
+    kmx, kmy, kmz = kmult if isinstance(kmult, tuple) else (kmult, kmult, kmult)
+    f = amp * np.sin(2 * np.pi * (2 * kmx) * x / sx)
     if sy > 1:
-        f = f * np.cos(2 * np.pi * (3 * kmult) * y / sy)
+        f = f * np.cos(2 * np.pi * (3 * kmy) * y / sy)
     if sz > 1:
-        f = f * np.cos(2 * np.pi * kmult * z / sz)
+        f = f * np.cos(2 * np.pi * kmz * z / sz)
     return (f + noise * (2 * rng.random((sz, sy, sx)) - 1)).astype(np.float32)
 
 
@@ -147,6 +148,24 @@ CASES = {
                        # the stresses after 100 steps, and the reference's own float32 run 0.7e-5 / 0.8e-5 / 2.5e-5
                        # (tests/golden/f32_floor.py).  Tolerances = 1.5 x that floor; the dynamic field and its gradients keep 1e-5.
                        tol=dict(sigxx=1.5e-5, sigxy=1.5e-5, P=1.5e-5, vx=3.6e-5, vy=6e-5, w=2.1e-4)),
+    # generic ("stash") x pass on long lines -- the one-job kernel (kernels_xs.cu: sx = 1024, 2048, 4096): products of DIFFERENT
+    # fields, three inputs shared by two outputs (different prefactors), in 2-D and 3-D; Model H with an sx = 2048 line, where
+    # phi^3 keeps the single-input kernel and the advection term gets a launch of its own (disjoint inputs)
+    "mixed2d_2048x16": dict(shape=(2048, 16, 1), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqyu", 0)], params=dict(l=0.5, m=0.25),
+                            eqs=["dt u + 0.5*q^2*u = l*iqxu*iqyu + m*q^2*u*iqxu - 0.125*q^2*iqyu^2", "iqxu = iqx*u", "iqyu = iqy*u"],
+                            ic=dict(u=("smooth", (1.0, 0.1, 1, 8))), steps=40, threads=0),
+    "mixed2d_1024x16": dict(shape=(1024, 16, 1), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqyu", 0)], params=dict(l=0.5, m=0.25),
+                            eqs=["dt u + 0.5*q^2*u = l*iqxu*iqyu + m*q^2*u*iqxu - 0.125*q^2*iqyu^2", "iqxu = iqx*u", "iqyu = iqy*u"],
+                            ic=dict(u=("smooth", (1.0, 0.1, 1, 4))), steps=40, threads=0),
+    "mixed2d_4096x8": dict(shape=(4096, 8, 1), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqyu", 0)], params=dict(l=0.5, m=0.25),
+                           eqs=["dt u + 0.5*q^2*u = l*iqxu*iqyu + m*q^2*u*iqxu - 0.125*q^2*iqyu^2", "iqxu = iqx*u", "iqyu = iqy*u"],
+                           ic=dict(u=("smooth", (1.0, 0.1, 1, 16))), steps=40, threads=0),
+    "mixed3d_1024x8x8": dict(shape=(1024, 8, 8), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqzu", 0)], params=dict(l=0.5, m=0.25),
+                             eqs=["dt u + 0.5*q^2*u = l*iqxu*iqzu*u + m*q^2*u*iqxu", "iqxu = iqx*u", "iqzu = iqz*u"],
+                             ic=dict(u=("smooth", (1.0, 0.1, 1, 4))), steps=30, threads=0),
+    "modelh_2048x64": dict(shape=(2048, 64, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
+                           ic=dict(phi=("smooth", (0.5, 0.025, 1, (32, 1, 1)))), steps=60, threads=0,   # 64 x 3 periods: the unstable band, as modelh_256
+                           tol=dict(sigxx=1.5e-5, sigxy=1.5e-5, P=1.5e-5, vx=3.6e-5, vy=6e-5, w=2.1e-4)),
     # config 04 (reduced size): Model H, 9 fields, constraint fields with implicit LHS (needs ORACLE-F)
     "modelh_32": dict(shape=(32, 32, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                       ic=dict(phi=("smooth", (0.5, 0.025))), steps=100),

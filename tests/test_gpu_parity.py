@@ -67,7 +67,8 @@ def test_reference_unit_tests_operators(built, dim, flavour):
                                   "modelh_32", "kpz3d_32_det", "kpz3d_128x16x16_det", "kpz2d_512x16_mixed_powers", "kpz3d_1024x16x8_det", "kpz2d_256x32_mixed_powers", "ops1d_16", "ops3d_16", "bc_even_inhomogeneous_64", "bc_odd_diffusion_64",
                                   "fcb_lowpass_ch2d_64", "fcb_asym_ch3d_16", "fcb_constraint_kpz2d_32", "fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64",
                                   "bc_clamp_product_64", "bc_clamp_product_1d_128", "ch2d_1024", "ch2d_64x4096", "modelh_256",
-                                  "ch3d_32x1024x8", "ch3d_32x8x2048", "kpz2d_128x2048_det", "ch3d_32x64x64"])
+                                  "ch3d_32x1024x8", "ch3d_32x8x2048", "kpz2d_128x2048_det", "ch3d_32x64x64",
+                                  "mixed2d_2048x16", "mixed2d_1024x16", "mixed2d_4096x8", "mixed3d_1024x8x8", "modelh_2048x64"])
 def test_parity_with_compiled_reference(built, name):
     case = CASES[name]
     lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F
@@ -531,6 +532,13 @@ def _run_variant(name, env, path):
     ("kpz3d_32_det", {"CUPSS_B200_ZCHUNK": "8"}, True),
     ("ch3d_512x8x8", {"CUPSS_B200_X3_NOPRUNE": "1"}, False),      # pruned strided level of the x pass: other rounding, same transform
     ("ch3d_512x8x8", {"CUPSS_B200_NO_GRAPH": "1"}, True),
+    ("mixed2d_2048x16", {"CUPSS_B200_NO_XS1": "1"}, True),         # one-job stash x pass vs the two-job kernel: the same arithmetic per line
+    ("mixed3d_1024x8x8", {"CUPSS_B200_NO_XS1": "1"}, True),
+    ("modelh_2048x64", {"CUPSS_B200_NO_XS1": "1"}, True),          # ... and the other grouping of the product terms
+    ("modelh_2048x64", {"CUPSS_B200_XS_OB": "2", "CUPSS_B200_XS_TWG": "0", "CUPSS_B200_XS_NT": "128"}, True),   # its launch variants
+    ("mixed2d_4096x8", {"CUPSS_B200_XS_OB": "2", "CUPSS_B200_XS_NT": "512"}, True),
+    ("modelh_2048x64", {"CUPSS_B200_NO_FANOUT": "1"}, True),       # independent launches side by side on the lanes vs one after the other
+    ("modelh_32", {"CUPSS_B200_NO_FANOUT": "1"}, True),
 ])
 def test_environment_variants_agree_with_the_default_path(built, tmp_path, name, env, bitwise):
     """The switchable code paths (README.md: environment switches) produce the default path's result: bit for bit where the
