@@ -200,13 +200,27 @@ static std::string jit_source(const cupss::KStageD& ks, int L) {
     return s;
 }
 
+// the lean evaluator with a signature that is not compiled into the library (a noisy field): same kernel body, SIG a constant
+static std::string jit_source_lean(int L, int sig) {
+    char b[1024];
+    std::string s = "#include \"kernels_axis.cuh\"\n";
+    if (cupss::axis_cluster_size(L) > 1) snprintf(b, sizeof b, "extern \"C\" __global__ void __cluster_dims__(cupss::AxisCfg<%d>::CL, 1, 1) __launch_bounds__(cupss::AxisCfg<%d>::THREADS, (cupss::AxisCfg<%d>::MINB > 2 ? 2 : cupss::AxisCfg<%d>::MINB))\n", L, L, L, L);
+    else if (const char* mb = getenv("CUPSS_B200_LEAN_NOISE_MINB")) snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(cupss::AxisCfg<%d>::THREADS, %d)\n", L, atoi(mb));
+    else snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(cupss::AxisCfg<%d>::THREADS, cupss::AxisCfg<%d>::MINB)\n", L, L);
+    s += b;
+    s += "jit_kstage(const __grid_constant__ cupss::AxisArgs a, const __grid_constant__ cupss::KStageD ks) {\n";
+    snprintf(b, sizeof b, "    cupss::axis_kstage_body<%d, cupss::KS_SCALAR_Q2, %d, void>(a, ks);\n}\n", L, sig);
+    s += b;
+    return s;
+}
+
 // NVRTC only (no driver API needed): source -> cubin.  Used by the engine and by the GPU-less self test.
 static bool jit_compile(const std::string& src, std::vector<char>* cubin, std::string* why);
 
 // Returns the CUfunction of the specialised kernel, or nullptr (with the reason in `why`) if it cannot be built.
-static void* jit_kstage_function(const cupss::KStageD& ks, int L, std::string* why) {
+static void* jit_kstage_function(const cupss::KStageD& ks, int L, std::string* why, int leanSig = -1) {
     if (!jit_load()) { *why = "NVRTC / driver API / kernel sources not available"; return nullptr; }
-    const std::string src = jit_source(ks, L);
+    const std::string src = leanSig >= 0 ? jit_source_lean(L, leanSig) : jit_source(ks, L);
     auto it = g_jit.cache.find(src);
     if (it != g_jit.cache.end()) return it->second;
     std::vector<char> cubin;
@@ -1252,8 +1266,10 @@ struct cupss_b200_plan {
         for (int o = 0; o < ks.nout; ++o) if (ks.out[o].noisy && ks.out[o].noise.invq) ks.usesInvq = 1;
         // lean evaluator when the sweep is a single noise-free dynamic field whose prefactors depend on q^2 only
         ks.fastKind = KS_GENERIC;
-        if (ks.nout == 1 && ks.out[0].dynamic && !ks.out[0].noisy && ks.nsrc == 1 && extraInv.empty() && nterm <= 1 &&
-            ks.out[0].nimp <= 4 && !getenv("CUPSS_B200_GENERIC_KSTAGE")) {
+        // (a noisy field: the lean evaluator compiled at run time for its signature, if its noise amplitude needs q^2 only)
+        const bool leanNoise = ks.nout == 1 && ks.out[0].noisy;
+        if (ks.nout == 1 && ks.out[0].dynamic && (!leanNoise || (ks.out[0].noise.invq == 0 && FftLevelsN(k.L) > 1 && !getenv("CUPSS_B200_NO_LEAN_NOISE"))) &&
+            ks.nsrc == 1 && extraInv.empty() && nterm <= 1 && ks.out[0].nimp <= 4 && !getenv("CUPSS_B200_GENERIC_KSTAGE")) {
             bool ok = true;
             for (int i = 0; i < npres; ++i)
                 if (ks.pres[i].iqx || ks.pres[i].iqy || ks.pres[i].iqz || ks.pres[i].invq || ks.pres[i].q2n < 0 || ks.pres[i].q2n > 3) ok = false;
@@ -1270,6 +1286,15 @@ struct cupss_b200_plan {
                 q.nimp = ks.out[0].nimp;
                 for (int i = 0; i < q.nimp; ++i) { q.ipre[i] = (double)ks.pres[ks.out[0].impOff + i].pre; q.in[i] = ks.pres[ks.out[0].impOff + i].q2n; }
                 ks.fastKind = KS_SCALAR_Q2;
+                if (leanNoise) {
+                    const char* je = getenv("CUPSS_B200_JIT");
+                    std::string why = "CUPSS_B200_JIT=0";
+                    if (!(je && je[0] == '0')) k.jitFn = jit_kstage_function(ks, k.L, &why, sq2_signature(q) | SQ2_SIG_NOISE);
+                    if (!k.jitFn) {   // no NVRTC: the generic evaluator (below) takes the sweep
+                        if (getenv("CUPSS_B200_VERBOSE")) fprintf(stderr, "cupss_b200: lean noisy k stage not compiled (%s)\n", why.c_str());
+                        ks.fastKind = KS_GENERIC;
+                    }
+                }
             }
         }
         if (ks.fastKind == KS_GENERIC) {
@@ -1812,6 +1837,15 @@ int cupss_b200_jit_selftest(char* log, int loglen) {
         if (!jit_compile(jit_source(ks, L), &cubin, &why)) {
             if (log && loglen > 0) snprintf(log, loglen, "L=%d: %s", L, why.c_str());
             return fail(CUPSS_B200_ERR_CUDA, "plan-specialised k stage does not compile for L=%d", L);
+        }
+    }
+    // the lean evaluator of a noisy field (KPZ: one fused term with a constant prefactor, q^2 on the left-hand side)
+    for (int L : {512, 1024, 32}) {
+        std::vector<char> cubin;
+        std::string why;
+        if (!jit_compile(jit_source_lean(L, sq2_sig(1, 0, 0, 0, 1, 1, 0, 0, 0, 1) | SQ2_SIG_NOISE), &cubin, &why)) {
+            if (log && loglen > 0) snprintf(log, loglen, "lean noisy k stage, L=%d: %s", L, why.c_str());
+            return fail(CUPSS_B200_ERR_CUDA, "lean noisy k stage does not compile for L=%d", L);
         }
     }
     if (log && loglen > 0) snprintf(log, loglen, "ok");

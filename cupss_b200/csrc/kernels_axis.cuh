@@ -511,7 +511,11 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
     const int nyFix = iyFix > ks.sy / 2 ? ks.sy - iyFix : iyFix;
     const bool keepY = od0.inv && (a.axis != 2 || nyFix <= od0.cuty);
     const bool keepA = keepY && (int)col <= od0.cutx, keepB = keepY && (int)col + 1 <= od0.cutx;
-    const unsigned int step = (KIND != KS_SCALAR_Q2 && ks.stepCounter) ? *ks.stepCounter : 0u;
+    // lean evaluator of a noisy field (run-time compiled signatures only): the noise of the thread's modes is generated in a
+    // rolled loop into the tile slots the thread has just emptied, and picked up by the unrolled evaluator below
+    constexpr bool NOISE = KIND == KS_SCALAR_Q2 && SIG >= 0 && (SIG & SQ2_SIG_NOISE) != 0;
+    static_assert(!NOISE || n > 1, "the noisy lean evaluator parks its noise in the tile");
+    const unsigned int step = ((KIND != KS_SCALAR_Q2 || NOISE) && ks.stepCounter) ? *ks.stepCounter : 0u;
 
     // ---- fused level: last forward butterfly -> k stage -> first inverse butterfly
 #pragma unroll 1
@@ -522,12 +526,13 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
         const unsigned rowStride = (L / R) * krs;
         const unsigned off0 = kbase + f0 * krs;
         float4 self[KIND == KS_SCALAR_Q2 ? R : 1];
-        if constexpr (KIND == KS_SCALAR_Q2) {
+        auto load_self = [&]() {
             const float2* sp = ks.src[0] + off0;
 #pragma unroll
             for (unsigned q = 0; q < R; ++q)
                 self[q] = __ldcg(reinterpret_cast<const float4*>(sp + q * rowStride));   // columns up to the pitch exist: no predicate, stores are guarded
-        }
+        };
+        if constexpr (KIND == KS_SCALAR_Q2 && !NOISE) load_self();   // (a noisy field: after the noise loop, which needs the registers)
         if (ks.hasFwd) {
 #pragma unroll
             for (unsigned q = 0; q < R; ++q) {
@@ -542,6 +547,43 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
             for (unsigned q = 0; q < R; ++q) { x0[q] = make_float2(0.0f, 0.0f); x1[q] = make_float2(0.0f, 0.0f); }
         }
 
+        if constexpr (NOISE) {
+            // noise increments amp * xi of the thread's modes (row f0 + (L/R) q; columns col, col + 1): one generator call per
+            // column pair, the Hermitian planes kx = 0, sx/2 through white_noise_mode -- the same calls, in the same arithmetic,
+            // as the generic evaluator makes
+            const bool ampQ = od0.noise.q2n != 0;   // conserved noise: the amplitude follows q^2
+#pragma unroll 1
+            for (unsigned q = 0; q < R; ++q) {
+                const int row = (int)(f0 + (L / R) * q);
+                KPoint ka{}, kb{};
+                ka.ix = (int)col; kb.ix = (int)col + 1;
+                ka.iy = kb.iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0);
+                ka.iz = kb.iz = a.axis == 2 ? row : 0;
+                ka.rndField = kb.rndField = -1;
+                float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (valid) {
+                    unsigned int c[4];
+                    philox_pair(ks, (int)(col >> 1), ka.iy, ka.iz, (unsigned int)od0.fieldId, step, c);
+                    ka.rnd0 = c[0]; ka.rnd1 = c[1]; kb.rnd0 = c[2]; kb.rnd1 = c[3];
+                    ka.rndField = kb.rndField = od0.fieldId;
+                    float ampA = od0.noiseAmp0, ampB = od0.noiseAmp0;
+                    if (ampQ) {
+                        const float qr = wavenumber(row, sRow, stepRow);
+                        const float qr2 = CUPSS_FMUL(qr, qr);
+                        ampA = noise_amplitude_q2(od0.noise, od0.noiseAmp0, CUPSS_FADD(baseA, qr2));
+                        ampB = noise_amplitude_q2(od0.noise, od0.noiseAmp0, CUPSS_FADD(baseB, qr2));
+                    }
+                    const float2 ga = white_noise_mode(ks, ka, od0.fieldId, step);
+                    g.x = CUPSS_FMUL(ampA, ga.x); g.y = CUPSS_FMUL(ampA, ga.y);
+                    if (valid1) {
+                        const float2 gb = white_noise_mode(ks, kb, od0.fieldId, step);
+                        g.z = CUPSS_FMUL(ampB, gb.x); g.w = CUPSS_FMUL(ampB, gb.y);
+                    }
+                }
+                tile[(v * R + q) * CP + cp] = g;
+            }
+            load_self();
+        }
         if constexpr (KIND == KS_SCALAR_Q2) {
             float2* dp = ks.dst[0] + off0;
             const double tp[3] = {ks.sq2.tpre[0], ks.sq2.tpre[1], ks.sq2.tpre[2]};
@@ -563,7 +605,11 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                 const float q2a = CUPSS_FADD(baseA, qr2);
                 const float q2b = CUPSS_FADD(baseB, qr2);
                 float2 va, vb;
-                if constexpr (SIG >= 0) {
+                if constexpr (NOISE) {
+                    const float4 g = tile[(v * R + q) * CP + cp];
+                    va = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2a, x0[q], make_float2(self[q].x, self[q].y), make_float2(g.x, g.y));
+                    vb = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2b, x1[q], make_float2(self[q].z, self[q].w), make_float2(g.z, g.w));
+                } else if constexpr (SIG >= 0) {
                     va = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2a, x0[q], make_float2(self[q].x, self[q].y));
                     vb = kstage_point_scalar_q2_sig<SIG>(tp, ip, termFused, dt, q2b, x1[q], make_float2(self[q].z, self[q].w));
                 } else {

@@ -406,6 +406,48 @@ def test_noise_3d_conserved_amplitude_follows_q2(built):
     ev.close()
 
 
+_NOISY_CODE = ("import sys, os; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+               "import numpy as np\n"
+               "from cupss_b200.capi import Evolver\n"
+               "shape = tuple(int(v) for v in sys.argv[1].split('x')); kind = sys.argv[2]\n"
+               "ev = Evolver(1, *shape, 1.0, 1.0, 1.0, 0.01)\n"
+               "if kind == 'kpz':\n"
+               "    fields = [('h', 1), ('iqxh', 0), ('iqyh', 0)] + ([('iqzh', 0)] if shape[2] > 1 else [])\n"
+               "    for f, d in fields: ev.createField(f, d)\n"
+               "    ev.addParameter('l', 0.5); ev.addParameter('D', 0.5)\n"
+               "    ev.addEquation('dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2' + (' + l*iqzh^2' if shape[2] > 1 else ''))\n"
+               "    for f, _ in fields[1:]: ev.addEquation('%%s = %%s*h' %% (f, f[:3]))\n"
+               "    ev.addNoise('h', '2*D')\n"
+               "else:\n"   # conserved noise on a Cahn-Hilliard field (Model B): amplitude ~ sqrt(q^2), fused inverse in the same kernel
+               "    ev.createField('phi', 1)\n"
+               "    ev.addParameter('D', 0.1)\n"
+               "    ev.addEquation('dt phi + q^2*(-1 + 4*q^2)*phi = - q^2*phi^3')\n"
+               "    ev.addNoise('phi', '2*D*q^2')\n"
+               "rng = np.random.default_rng(3)\n"
+               "name = 'h' if kind == 'kpz' else 'phi'\n"
+               "ev.setReal(name, (0.2 * (2 * rng.random(shape[::-1]) - 1)).astype(np.float32))\n"
+               "ev.setNoiseSeed(4242)\n"
+               "ev.prepareProblem(); ev.advanceTime(12); ev.copyAllDataToHost()\n"
+               "np.save(sys.argv[3], ev.real(name)); ev.close()\n") % (ROOT, os.path.join(ROOT, "tests"))
+
+
+@pytest.mark.parametrize("shape,kind", [("64x32x32", "kpz"), ("32x16x1024", "kpz"), ("64x64x1", "kpz"), ("64x32x32", "modelb"), ("32x2048x1", "modelb")])
+def test_lean_noisy_kstage_equals_the_generic_evaluator_bitwise(built, tmp_path, shape, kind):
+    """A noisy field whose prefactors depend on q^2 only runs the lean evaluator compiled at run time for its signature
+    (kernels_axis.cuh: NOISE); the generic evaluator (interpreter / plan-specialised) draws the same numbers and rounds the
+    same way: bit-identical fields, incl. the cluster-shared axes and the conserved (q^2) amplitude."""
+    out = {}
+    for tag, env in (("lean", {}), ("generic", {"CUPSS_B200_NO_LEAN_NOISE": "1"}), ("interp", {"CUPSS_B200_NO_LEAN_NOISE": "1", "CUPSS_B200_JIT": "0"})):
+        e = dict(os.environ); e.update(env)
+        path = str(tmp_path / (tag + ".npy"))
+        r = subprocess.run([sys.executable, "-c", _NOISY_CODE, shape, kind, path], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[tag] = np.load(path)
+    assert np.isfinite(out["lean"]).all() and out["lean"].std() > 0
+    assert np.array_equal(out["generic"], out["interp"])
+    assert np.array_equal(out["lean"], out["generic"]), rel_l2(out["lean"], out["generic"])
+
+
 def test_noise_stream_is_reproducible_and_seed_dependent(built):
     from cupss_b200.capi import Evolver
 
