@@ -411,6 +411,9 @@ axis_plain_cluster_kernel(const __grid_constant__ AxisArgs a) {
     tile_level<S, n - 1, DIR, TV, true>(tv, twS, sld, gst);
 }
 
+template <class PLAN> struct PlanNsrc { static constexpr int value = PLAN::nsrc; };
+template <> struct PlanNsrc<void> { static constexpr int value = 0; };
+
 // PLAN: compile-time structure of the sweep for KIND == KS_JIT (kstage.cuh), void otherwise.
 // A cluster-shared axis (AxisCfg<L>::CL > 1): the CTA runs the S = 512-point levels on its own block between the two cross
 // levels; position p of CTA c's block holds frequency row c + CL * freq_of_pos<S>(p), so with q unrolled the row of the
@@ -628,6 +631,17 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                 x1[q] = (keepB && keepR) ? vb : make_float2(0.0f, 0.0f);
             }
         } else {
+            // run-time compiled plan: the pointwise sources of the NEXT row are requested (one 128-bit load per source for the
+            // column pair) before this row is evaluated -- the rolled loop otherwise pays one exposed load latency per row
+            // (KPZ-3D 512^3 constraint sweep: 59 % of the stall samples on the first use of the state, profiles/README.md)
+            constexpr int NSRC = PlanNsrc<PLAN>::value;
+            float4 pre[NSRC > 0 ? NSRC : 1];
+            auto fetch_sources = [&](unsigned q) {
+                const unsigned o = kbase + (f0 + (unsigned)(L / R) * q) * krs;
+#pragma unroll
+                for (int i = 0; i < NSRC; ++i) pre[i] = valid ? ld4(ks.src[i] + o) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            };
+            if constexpr (KIND == KS_JIT) fetch_sources(0);
 #pragma unroll 1
             for (unsigned q = 0; q < R; ++q) {
                 const int row = (int)(f0 + (L / R) * q);
@@ -635,6 +649,12 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                 const int iz = a.axis == 2 ? row : 0;
                 const long long off = (long long)(kbase + (unsigned)row * krs);
                 float2 ra = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
+                float2 sa[NSRC > 0 ? NSRC : 1], sb[NSRC > 0 ? NSRC : 1];
+                if constexpr (KIND == KS_JIT) {
+#pragma unroll
+                    for (int i = 0; i < (NSRC > 0 ? NSRC : 1); ++i) { sa[i] = make_float2(pre[i].x, pre[i].y); sb[i] = make_float2(pre[i].z, pre[i].w); }
+                    if (q + 1 < R) fetch_sources(q + 1);
+                }
                 KPoint ka = make_kpoint(ks, (int)col, iy, iz), kb = make_kpoint(ks, (int)col + 1, iy, iz);
                 if (ks.noiseField >= 0 && valid) {   // one generator call for both columns of the pair
                     unsigned int c[4];
@@ -643,8 +663,8 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                     ka.rndField = kb.rndField = ks.noiseField;
                 }
                 if constexpr (KIND == KS_JIT) {
-                    if (valid) ra = kstage_point_plan<PLAN>(ks, ka, x0[0], off, step);
-                    if (valid1) rb = kstage_point_plan<PLAN>(ks, kb, x1[0], off + 1, step);
+                    if (valid) ra = kstage_point_plan_src<PLAN>(ks, ka, x0[0], off, step, sa);
+                    if (valid1) rb = kstage_point_plan_src<PLAN>(ks, kb, x1[0], off + 1, step, sb);
                 } else {
                     if (valid) ra = kstage_point(ks, ka, x0[0], off, step);
                     if (valid1) rb = kstage_point(ks, kb, x1[0], off + 1, step);
