@@ -413,6 +413,8 @@ axis_plain_cluster_kernel(const __grid_constant__ AxisArgs a) {
 
 template <class PLAN> struct PlanNsrc { static constexpr int value = PLAN::nsrc; };
 template <> struct PlanNsrc<void> { static constexpr int value = 0; };
+template <class PLAN> struct PlanNout { static constexpr int value = PLAN::nout; };
+template <> struct PlanNout<void> { static constexpr int value = 0; };
 
 // PLAN: compile-time structure of the sweep for KIND == KS_JIT (kstage.cuh), void otherwise.
 // A cluster-shared axis (AxisCfg<L>::CL > 1): the CTA runs the S = 512-point levels on its own block between the two cross
@@ -552,23 +554,19 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
 
         if constexpr (NOISE) {
             // noise increments amp * xi of the thread's modes (row f0 + (L/R) q; columns col, col + 1): one generator call per
-            // column pair, the Hermitian planes kx = 0, sx/2 through white_noise_mode -- the same calls, in the same arithmetic,
-            // as the generic evaluator makes
+            // column pair -- the same calls, in the same arithmetic, as the generic evaluator makes.  Columns inside the
+            // self-conjugate planes kx = 0, sx/2 (one lane of the first and of the last column tile) take white_noise_mode with
+            // its mirror-row logic; every other pair is two Box-Muller transforms of the four words.
             const bool ampQ = od0.noise.q2n != 0;   // conserved noise: the amplitude follows q^2
+            const bool planes = col == 0u || 2 * (int)col == ks.sx || 2 * ((int)col + 1) == ks.sx;
 #pragma unroll 1
             for (unsigned q = 0; q < R; ++q) {
                 const int row = (int)(f0 + (L / R) * q);
-                KPoint ka{}, kb{};
-                ka.ix = (int)col; kb.ix = (int)col + 1;
-                ka.iy = kb.iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0);
-                ka.iz = kb.iz = a.axis == 2 ? row : 0;
-                ka.rndField = kb.rndField = -1;
+                const int iy = a.axis == 2 ? iyFix : (a.axis == 1 ? row : 0), iz = a.axis == 2 ? row : 0;
                 float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (valid) {
                     unsigned int c[4];
-                    philox_pair(ks, (int)(col >> 1), ka.iy, ka.iz, (unsigned int)od0.fieldId, step, c);
-                    ka.rnd0 = c[0]; ka.rnd1 = c[1]; kb.rnd0 = c[2]; kb.rnd1 = c[3];
-                    ka.rndField = kb.rndField = od0.fieldId;
+                    philox_pair(ks, (int)(col >> 1), iy, iz, (unsigned int)od0.fieldId, step, c);
                     float ampA = od0.noiseAmp0, ampB = od0.noiseAmp0;
                     if (ampQ) {
                         const float qr = wavenumber(row, sRow, stepRow);
@@ -576,12 +574,21 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                         ampA = noise_amplitude_q2(od0.noise, od0.noiseAmp0, CUPSS_FADD(baseA, qr2));
                         ampB = noise_amplitude_q2(od0.noise, od0.noiseAmp0, CUPSS_FADD(baseB, qr2));
                     }
-                    const float2 ga = white_noise_mode(ks, ka, od0.fieldId, step);
-                    g.x = CUPSS_FMUL(ampA, ga.x); g.y = CUPSS_FMUL(ampA, ga.y);
-                    if (valid1) {
-                        const float2 gb = white_noise_mode(ks, kb, od0.fieldId, step);
-                        g.z = CUPSS_FMUL(ampB, gb.x); g.w = CUPSS_FMUL(ampB, gb.y);
+                    float2 ga, gb = make_float2(0.0f, 0.0f);
+                    if (!planes) {
+                        ga = normal2_from_words(c[0], c[1]);
+                        gb = normal2_from_words(c[2], c[3]);
+                        ga.x *= ks.whitePair; ga.y *= ks.whitePair; gb.x *= ks.whitePair; gb.y *= ks.whitePair;
+                    } else {
+                        KPoint ka{}, kb{};
+                        ka.ix = (int)col; kb.ix = (int)col + 1;
+                        ka.iy = kb.iy = iy; ka.iz = kb.iz = iz;
+                        ka.rnd0 = c[0]; ka.rnd1 = c[1]; kb.rnd0 = c[2]; kb.rnd1 = c[3];
+                        ka.rndField = kb.rndField = od0.fieldId;
+                        ga = white_noise_mode(ks, ka, od0.fieldId, step);
+                        if (valid1) gb = white_noise_mode(ks, kb, od0.fieldId, step);
                     }
+                    g = make_float4(CUPSS_FMUL(ampA, ga.x), CUPSS_FMUL(ampA, ga.y), CUPSS_FMUL(ampB, gb.x), CUPSS_FMUL(ampB, gb.y));
                 }
                 tile[(v * R + q) * CP + cp] = g;
             }
@@ -663,8 +670,24 @@ __device__ __forceinline__ void axis_kstage_body(const AxisArgs& a, const KStage
                     ka.rndField = kb.rndField = ks.noiseField;
                 }
                 if constexpr (KIND == KS_JIT) {
-                    if (valid) ra = kstage_point_plan_src<PLAN>(ks, ka, x0[0], off, step, sa);
-                    if (valid1) rb = kstage_point_plan_src<PLAN>(ks, kb, x1[0], off + 1, step, sb);
+                    // up to four outputs: the new values of both columns go out with one 128-bit store per output (KPZ-3D 512^3
+                    // constraint sweep 0.70 -> 0.60 ms); more outputs cost more in registers than the stores save (Model H 2048^2,
+                    // eight outputs: 0.102 -> 0.119 ms) and are stored mode by mode
+                    constexpr int NOUT = PlanNout<PLAN>::value;
+                    if constexpr (NOUT <= 4) {
+                        float2 oa[NOUT > 0 ? NOUT : 1], ob[NOUT > 0 ? NOUT : 1];
+#pragma unroll
+                        for (int o = 0; o < NOUT; ++o) ob[o] = make_float2(0.0f, 0.0f);   // padding column of the pitch
+                        if (valid) ra = kstage_point_plan_src<PLAN>(ks, ka, x0[0], off, step, sa, oa);
+                        if (valid1) rb = kstage_point_plan_src<PLAN>(ks, kb, x1[0], off + 1, step, sb, ob);
+                        if (valid) {
+#pragma unroll
+                            for (int o = 0; o < NOUT; ++o) st4(ks.dst[o] + off, make_float4(oa[o].x, oa[o].y, ob[o].x, ob[o].y));
+                        }
+                    } else {
+                        if (valid) ra = kstage_point_plan_src<PLAN>(ks, ka, x0[0], off, step, sa);
+                        if (valid1) rb = kstage_point_plan_src<PLAN>(ks, kb, x1[0], off + 1, step, sb);
+                    }
                 } else {
                     if (valid) ra = kstage_point(ks, ka, x0[0], off, step);
                     if (valid1) rb = kstage_point(ks, kb, x1[0], off + 1, step);
