@@ -103,6 +103,32 @@ def main():
     check("noise default-seed real", part[rank * zl:(rank + 1) * zl], single[rank * zl:(rank + 1) * zl])
     check("noise default-seed fieldsFourier", part_c[rank * zl:(rank + 1) * zl], single_c[rank * zl:(rank + 1) * zl])
 
+    # KPZ with noise (BASELINE.json configs[4] in small): the lean noisy evaluator next to the fused exchange, incl. a z axis
+    # that a cluster shares -- bit-identical to one GPU
+    def kpz_noisy(partition, shape):
+        ev = Evolver(1, *shape, 1.0, 1.0, 1.0, 0.01)
+        for f, d in (("h", 1), ("iqxh", 0), ("iqyh", 0), ("iqzh", 0)):
+            ev.createField(f, d)
+        ev.addParameter("l", 0.5)
+        ev.addParameter("D", 0.5)
+        for e in ("dt h + 0.5*q^2*h = l*iqxh^2 + l*iqyh^2 + l*iqzh^2", "iqxh = iqx*h", "iqyh = iqy*h", "iqzh = iqz*h"):
+            ev.addEquation(e)
+        ev.addNoise("h", "2*D")
+        ev.setReal("h", cases.smooth_ic(*shape, 1.0, 0.1))
+        if partition:
+            ev.setPartition(rank, world, unique_id())
+        ev.setNoiseSeed(777)
+        ev.prepareProblem()
+        ev.advanceTime(6)
+        ev.copyAllDataToHost()
+        out = ev.real("h")
+        ev.close()
+        return out
+    for shape in ((64, 32, 32), (32, 16, 1024)):
+        zs = shape[2] // world
+        got, want = kpz_noisy(True, shape), kpz_noisy(False, shape)
+        check(f"kpz noisy {shape}", got[rank * zs:(rank + 1) * zs], want[rank * zs:(rank + 1) * zs])
+
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag.item()) == 1:
