@@ -163,6 +163,8 @@ CASES = {
     "mixed3d_1024x8x8": dict(shape=(1024, 8, 8), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqzu", 0)], params=dict(l=0.5, m=0.25),
                              eqs=["dt u + 0.5*q^2*u = l*iqxu*iqzu*u + m*q^2*u*iqxu", "iqxu = iqx*u", "iqzu = iqz*u"],
                              ic=dict(u=("smooth", (1.0, 0.1, 1, 4))), steps=30, threads=0),
+    "mixed1d_2048": dict(shape=(2048, 1, 1), dt=0.01, fields=[("u", 1), ("w", 0)], params=dict(nu=0.5),   # a single line: the pair's second line does not exist
+                         eqs=["dt u + nu*q^2*u = -u*w + 0.1*q^2*w*w*u", "w = iqx*u"], ic=dict(u=("smooth", (0.5, 0.05, 1, 8))), steps=60, threads=0),
     "modelh_2048x64": dict(shape=(2048, 64, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,
                            ic=dict(phi=("smooth", (0.5, 0.025, 1, (32, 1, 1)))), steps=60, threads=0,   # 64 x 3 periods: the unstable band, as modelh_256
                            tol=dict(sigxx=1.5e-5, sigxy=1.5e-5, P=1.5e-5, vx=3.6e-5, vy=6e-5, w=2.1e-4)),
