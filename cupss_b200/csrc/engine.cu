@@ -1214,8 +1214,19 @@ struct cupss_b200_plan {
             OutD& od = ks.out[ks.nout];
             od = OutD{};
             od.dynamic = F.dynamic; od.fieldId = (signed char)f;
-            const int self = srcField(f);
-            if (self < 0) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
+            // The old value of the field itself is a source only where the evaluator uses it: a dynamic field (Euler update) or a
+            // constraint field without a right-hand side term (it keeps its value).  A constraint field WITH terms is assigned
+            // from them (kstage.cuh), so registering its spectrum would only cost loads and inflate the byte model.
+            size_t emitted = 0;
+            for (size_t ti = 0; ti < F.terms.size(); ++ti) {
+                if (F.terms[ti].product.size() == 1) { ++emitted; continue; }
+                for (size_t g = 0; g < groups.size(); ++g) if (groups[g].field == f && groups[g].firstTerm == (int)ti) ++emitted;
+            }
+            int self = -1;
+            if (F.dynamic || emitted == 0) {
+                self = srcField(f);
+                if (self < 0) return fail(CUPSS_B200_ERR_ARG, "too many k-stage sources");
+            }
             od.selfSrc = (signed char)self;
             od.dst = (signed char)ks.nout;
             ks.dst[ks.nout] = F.S;
