@@ -5,9 +5,9 @@
 // evaluated point by point, forward as decimation in time) -- results are bit-identical -- but a slot is ONE job (a pair of
 // lines, float2 elements) instead of two interleaved jobs (float4): at sx = 2048 a slot of the two-job kernel with its stash
 // fills an SM's shared memory (37 KB per buffer, 1 + nIn buffers: one 256-thread CTA per SM, every phase exposed -- Model H
-// 2048^2: 11-14 % of the HBM roofline, profiles/README.md).  Here a buffer is 17 KB, a CTA has SX / 16 threads (every thread
-// busy on the radix-16 levels) and two to four CTAs share an SM, so the global loads of one overlap the butterflies of the
-// others.  Replaces the same reference code as kernels_x.cu (/root/reference/src/field.cpp:247-298, src/term.cpp:48-102,
+// 2048^2: 11-14 % of the HBM roofline, profiles/README.md).  Here a buffer is 17 KB, the transforms of all inputs run side
+// by side in their stash buffers, a CTA has SX / 8 threads and two or three CTAs share an SM, so the global loads of one
+// overlap the butterflies of the others.  Replaces the same reference code as kernels_x.cu (/root/reference/src/field.cpp:247-298, src/term.cpp:48-102,
 // src/term_kernels.cu:48-70).
 #include <cstdlib>
 
@@ -246,7 +246,8 @@ static cudaError_t launch_xs(XArgs& a, cudaStream_t st) {
     a.jobsPerCta = ob;
     // twiddles through L1 by default: the shared-memory copy costs a prologue per CTA and, with a small stash, a CTA per SM
     // (Model H 2048^2: x_con 0.050 -> 0.042 ms, x_dyn 0.059 -> 0.057 ms)
-    const bool twg = twgEnv >= 0 ? twgEnv != 0 : true;
+    bool twg = twgEnv >= 0 ? twgEnv != 0 : true;
+    if (!twg && xs_smem<SX>(a.nIn, ob, false) > 226 * 1024) twg = true;   // the copy does not fit next to this many buffers
     if (nt == 2 * XsCfg<SX>::NT) return twg ? launch_xs2<SX, 2 * XsCfg<SX>::NT, true>(a, st) : launch_xs2<SX, 2 * XsCfg<SX>::NT, false>(a, st);
     return twg ? launch_xs2<SX, XsCfg<SX>::NT, true>(a, st) : launch_xs2<SX, XsCfg<SX>::NT, false>(a, st);
 }
