@@ -66,12 +66,17 @@ __global__ void __launch_bounds__(NT, (SX >= 4096 ? 512 : 768) / NT) xstash1_ker
             const unsigned b = w / NV, v = w % NV;
             float2* xb = bufs + b * XB;
             const unsigned blk = v / M, j = v % M, row0 = blk * N + j;
+            // xspad(row0 + M q) = xspad(row0) + xspad(M q): M q is a multiple of 8 and row0 mod 16 < 8 whenever M = 8 (j < 8, N a
+            // multiple of 16), so the low four bits never carry -- one padded base and compile-time offsets instead of a shift
+            // and an add per access
+            static_assert(M % 8 == 0 && N % 16 == 0, "padded offsets are folded at compile time");
+            float2* xr = xb + xspad(row0);
             float2 x[R];
 #pragma unroll
-            for (unsigned q = 0; q < R; ++q) x[q] = xb[xspad(row0 + M * q)];
+            for (unsigned q = 0; q < R; ++q) x[q] = xr[M * q + ((M * q) >> 4)];
             level_butterfly<SX, LV, SIGN, DIF>(x, j, twS);
 #pragma unroll
-            for (unsigned q = 0; q < R; ++q) xb[xspad(row0 + M * q)] = x[q];
+            for (unsigned q = 0; q < R; ++q) xr[M * q + ((M * q) >> 4)] = x[q];
         }
     };
     using std::integral_constant;
@@ -107,8 +112,10 @@ __global__ void __launch_bounds__(NT, (SX >= 4096 ? 512 : 768) / NT) xstash1_ker
                 x[q] = upper ? make_float2(A.x + B.y, B.x - A.y) : make_float2(A.x - B.y, A.y + B.x);
             }
             level_butterfly<SX, 0, +1, true>(x, v, twS);
+            float2* xr = xb + xspad(v);   // M is a multiple of 16 here: xspad(v + M q) = xspad(v) + xspad(M q)
+            static_assert(M % 16 == 0, "padded offsets are folded at compile time");
 #pragma unroll
-            for (unsigned q = 0; q < R; ++q) xb[xspad(v + M * q)] = x[q];
+            for (unsigned q = 0; q < R; ++q) xr[M * q + ((M * q) >> 4)] = x[q];
         }
     }
     __syncthreads();
