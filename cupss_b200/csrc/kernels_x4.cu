@@ -45,8 +45,16 @@ __device__ __forceinline__ void job_sync(unsigned job) {
     else asm volatile("bar.sync %0, %1;" ::"r"(job + 1u), "n"(TJ) : "memory");
 }
 
+// x[q] <- (-i)^q x[q] conj(w_sx^{j q}) for q >= 1, the twiddles read through L1 (entry (q-1)*M + j of the level-0 table)
+template <int R0, int M, int... Q>
+__device__ __forceinline__ void x4_twiddle_rot(float2 (&x)[R0], const float2* __restrict__ twj, cupss_std::integer_sequence<int, Q...>) {
+    ((x[Q] = Q == 0 ? x[Q] : cmul_conj_rot<Q % 4>(x[Q], __ldg(twj + (Q > 0 ? Q - 1 : 0) * M))), ...);
+}
+
 // POLY: c0*r^p0 + c1*r^p1 of the one input (powers up to 4) instead of the straight-line c*r^2 / c*r^3.
-template <int SX, bool POLY = false>
+// PRUNE: the input is known (launcher) to be band-limited to kx <= SX/4 -- the dealiased field of a cubic term, BASELINE.json
+// configs[1] -- and the inverse strided level runs PrunedDft (fft_core.cuh), as in the two-level kernel (kernels_x3.cu).
+template <int SX, bool POLY = false, bool PRUNE = false>
 __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __grid_constant__ XArgs a) {
     using Cfg = X4Cfg<SX>;
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1, R2 = Cfg::R2, M = Cfg::M0, N1 = Cfg::N1, M1 = Cfg::M1, TJ = Cfg::TJ, LB = Cfg::LB, H = R0 / 2;
@@ -68,7 +76,48 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
     // ------------------------------------------------ inverse, level 0: form C from the half-spectrum lines
     {
         float2 xA[R0], xB[R0];
-        {
+        if constexpr (PRUNE) {
+            constexpr int Q = R0 / 4;   // live: k = j + M q with q < Q, and k = M Q = SX/4 on row 0
+            const float2* pa = a.in[0] + lA * a.pitch;
+            const float2* pb = a.in[0] + lB * a.pitch;
+            auto form = [&](unsigned k, float2& c, float2& m) {   // c = A[k] + i B[k],  m = conj(A[k]) + i conj(B[k]) = C[sx - k]
+                float2 A = hasA ? __ldg(pa + k) : z;
+                float2 B = hasB ? __ldg(pb + k) : z;
+                if (k == 0) { A.y = 0.0f; B.y = 0.0f; }   // real-part projection of the self-conjugate bin
+                c = make_float2(A.x - B.y, A.y + B.x);
+                m = make_float2(A.x + B.y, B.x - A.y);
+            };
+            float2 cA[Q], mA[Q], cB[Q], mB[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                form(jA + M * q, cA[q], mA[q]);
+                form(jB + M * q, cB[q], mB[q]);
+            }
+            // k = SX/4 (row 0 only): predicated loads in the same burst as the others, zeros elsewhere
+            float2 ev, od;
+            {
+                const float2 A = (t0 && hasA) ? __ldg(pa + SX / 4) : z;
+                const float2 B = (t0 && hasB) ? __ldg(pb + SX / 4) : z;
+                const float2 c = make_float2(A.x - B.y, A.y + B.x), m = make_float2(A.x + B.y, B.x - A.y);
+                ev = cadd(m, c); od = csub(m, c);   // Y[p] += m + (-1)^p c
+            }
+            // upper ends x[R0-Q .. R0-1] of the two rows: the mirrors (same placement as the general branch, zeros dropped)
+            float2 hiA[Q], hiB[Q];
+#pragma unroll
+            for (int i = 0; i < Q; ++i) hiB[i] = t0 ? mB[Q - 1 - i] : mA[Q - 1 - i];
+            hiA[0] = t0 ? z : mB[Q - 1];   // row 0: x[R0-Q] is the mirror of k = SX/4, added below
+#pragma unroll
+            for (int i = 1; i < Q; ++i) hiA[i] = t0 ? mA[Q - i] : mB[Q - 1 - i];
+            PrunedDft<R0>::run(cA, hiA, xA);
+            PrunedDft<R0>::run(cB, hiB, xB);
+            if (t0) {
+#pragma unroll
+                for (int p2 = 0; p2 < R0; p2 += 2) { xA[p2] = cadd(xA[p2], ev); xA[p2 + 1] = cadd(xA[p2 + 1], od); }
+            }
+            // X[q] = (-i)^q Y[q]: the rotation rides on the twiddle multiplication
+            x4_twiddle_rot<R0, M>(xA, tw0 + jA, cupss_std::make_integer_sequence<int, R0>{});
+            x4_twiddle_rot<R0, M>(xB, tw0 + jB, cupss_std::make_integer_sequence<int, R0>{});
+        } else {
             const float2* pa = a.in[0] + lA * a.pitch;
             const float2* pb = a.in[0] + lB * a.pitch;
             const int kmax = a.kmax[0];
@@ -93,13 +142,13 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 4) xpass4_kernel(const __g
             xA[H] = t0 ? cMid : mB[H - 1];
 #pragma unroll
             for (int i = 1; i < H; ++i) xA[H + i] = t0 ? mA[H - i] : mB[H - 1 - i];
-        }
-        Dft<R0, +1>::run(xA);
-        Dft<R0, +1>::run(xB);
+            Dft<R0, +1>::run(xA);
+            Dft<R0, +1>::run(xB);
 #pragma unroll
-        for (int q = 1; q < R0; ++q) {
-            xA[q] = cmul_conj(xA[q], __ldg(tw0 + (q - 1) * M + jA));
-            xB[q] = cmul_conj(xB[q], __ldg(tw0 + (q - 1) * M + jB));
+            for (int q = 1; q < R0; ++q) {
+                xA[q] = cmul_conj(xA[q], __ldg(tw0 + (q - 1) * M + jA));
+                xB[q] = cmul_conj(xB[q], __ldg(tw0 + (q - 1) * M + jB));
+            }
         }
 #pragma unroll
         for (int q = 0; q < R0; ++q) {
@@ -415,20 +464,24 @@ __global__ void __launch_bounds__(X4Cfg<SX>::THREADS, 3) xpass4s_kernel(const __
     }
 }
 
-template <int SX, bool POLY = false>
+template <int SX, bool POLY = false, bool PRUNE = false>
 static cudaError_t launch_x4_size(XArgs& a, cudaStream_t st) {
     using Cfg = X4Cfg<SX>;
+    if constexpr (!POLY && !PRUNE) {   // band-limited to sx/4 (the dealiased field of a cubic term): pruned strided level
+        static const bool noPrune = [] { const char* e = getenv("CUPSS_B200_X4_NOPRUNE"); return e && e[0] == '1'; }();
+        if (a.kmax[0] == SX / 4 && !noPrune) return launch_x4_size<SX, false, true>(a, st);
+    }
     static bool attr = false;
     if (!attr) {
         if (Cfg::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xpass4_kernel<SX, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(xpass4_kernel<SX, POLY, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr = true;
     }
     const long long njobs = (a.nlines + 1) / 2;
     const unsigned grid = (unsigned)((njobs + Cfg::JOBS - 1) / Cfg::JOBS);
-    xpass4_kernel<SX, POLY><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    xpass4_kernel<SX, POLY, PRUNE><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 

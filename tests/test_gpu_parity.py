@@ -573,6 +573,9 @@ def _run_variant(name, env, path):
     ("ch3d_64x32x16", {"CUPSS_B200_ZCHUNK": "8", "CUPSS_B200_ZCHUNK_LANES": "1"}, True),
     ("kpz3d_32_det", {"CUPSS_B200_ZCHUNK": "8"}, True),
     ("ch3d_512x8x8", {"CUPSS_B200_X3_NOPRUNE": "1"}, False),      # pruned strided level of the x pass: other rounding, same transform
+    ("ch2d_4096x32", {"CUPSS_B200_X4_NOPRUNE": "1"}, False),     # ... and of the three-level kernel (sx = 256, 1024, 2048, 4096)
+    ("ch3d_1024x32x8", {"CUPSS_B200_X4_NOPRUNE": "1"}, False),
+    ("ch3d_256x16x8", {"CUPSS_B200_X4_NOPRUNE": "1"}, False),
     ("ch3d_512x8x8", {"CUPSS_B200_NO_GRAPH": "1"}, True),
     ("mixed2d_2048x16", {"CUPSS_B200_NO_XS1": "1"}, True),         # one-job stash x pass vs the two-job kernel: the same arithmetic per line
     ("mixed3d_1024x8x8", {"CUPSS_B200_NO_XS1": "1"}, True),
