@@ -1171,6 +1171,7 @@ struct cupss_b200_plan {
         ks.sx = sx; ks.sy = sy; ks.sz = sz;
         ks.stepCounter = stepCounter;
         ks.seed = 0;
+        philox_round_keys(0, ks.philoxKey);
         ks.noiseField = -1;
         ks.whiteSelf = std::sqrt((float)sx * (float)sy * (float)sz);
         ks.whitePair = std::sqrt(0.5f * ((float)sx * (float)sy * (float)sz));
@@ -1263,6 +1264,7 @@ struct cupss_b200_plan {
                 od.noise.pre = F.noise.pre; od.noise.q2n = (signed char)F.noise.q2n; od.noise.invq = (signed char)F.noise.invq;
                 od.noiseAmp0 = std::sqrt(ks.noiseBase * F.noise.pre);
                 ks.seed = F.seed;
+                philox_round_keys(F.seed, ks.philoxKey);
                 if (ks.noiseField < 0) ks.noiseField = f;
             }
             cutoffs(F.aliasOrder, &od.cutx, &od.cuty, &od.cutz);

@@ -27,6 +27,11 @@ static void kat() {
         philox4x32_10(c, t.k[0], t.k[1]);
         for (int i = 0; i < 4; ++i) CHECK(c[i] == t.want[i], "philox4x32_10 word %d: %08x, Random123 says %08x", i, c[i], t.want[i]);
         std::printf("philox4x32_10 -> %08x %08x %08x %08x\n", c[0], c[1], c[2], c[3]);
+        // the variant the step kernels call: round keys from a table (KStageD::philoxKey, in the constant bank on the device)
+        unsigned int rk[20], d[4] = {t.c[0], t.c[1], t.c[2], t.c[3]};
+        philox_round_keys((unsigned long long)t.k[0] | ((unsigned long long)t.k[1] << 32), rk);
+        philox4x32_10_keys(d, rk);
+        for (int i = 0; i < 4; ++i) CHECK(d[i] == t.want[i], "philox4x32_10_keys word %d: %08x, Random123 says %08x", i, d[i], t.want[i]);
     }
 }
 
@@ -35,6 +40,7 @@ static KStageD make_ks(int sx, int sy, int sz, unsigned long long seed) {
     ks.sx = sx; ks.sy = sy; ks.sz = sz;
     ks.stepqx = ks.stepqy = ks.stepqz = 1.0f;
     ks.seed = seed;
+    philox_round_keys(seed, ks.philoxKey);
     const float n = (float)sx * (float)sy * (float)sz;
     ks.whiteSelf = std::sqrt(n);
     ks.whitePair = std::sqrt(0.5f * n);
@@ -84,7 +90,7 @@ static void hermitian(int sx, int sy, int sz) {
     // streams: other field id, other step, other seed -> other numbers; same inputs -> same numbers
     const KPoint k = make_kpoint(ks, 1, 0, 0);
     const float2 r0 = white_noise_mode(ks, k, 3, 7), r1 = white_noise_mode(ks, k, 3, 7), r2 = white_noise_mode(ks, k, 4, 7), r3 = white_noise_mode(ks, k, 3, 8);
-    KStageD ks2 = ks; ks2.seed += 1;
+    KStageD ks2 = ks; ks2.seed += 1; philox_round_keys(ks2.seed, ks2.philoxKey);
     const float2 r4 = white_noise_mode(ks2, k, 3, 7);
     CHECK(r0.x == r1.x && r0.y == r1.y, "not reproducible");
     CHECK(r0.x != r2.x && r0.x != r3.x && r0.x != r4.x, "field / step / seed do not separate the streams");
