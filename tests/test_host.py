@@ -342,3 +342,30 @@ def test_reference_examples_compile_unchanged(built, tmp_path):
                    "-L", libdir, "-lcupss", "-L", engdir, "-lcupss_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-o", out]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, (s, r.stderr[-2000:])
+
+
+def test_one_job_stash_xpass_padded_offsets_fold():
+    """kernels_xs.cu addresses its padded lines as xspad(row0) + a compile-time offset per butterfly leg.  That is only the
+    same element as xspad(row0 + M*q) if the low four bits never carry; checked here for every virtual thread of every level of
+    the three line lengths the kernel is built for (radices as in fft_core.cuh: FftLevels), together with the claim that a half
+    warp's 64-bit accesses fall into 16 different banks on the consecutive and on the innermost (stride R) patterns."""
+    def xspad(i):
+        return i + (i >> 4)
+    for sx, rad in ((1024, (16, 8, 8)), (2048, (16, 16, 8)), (4096, (16, 16, 16))):
+        n = sx
+        for lv, r in enumerate(rad[:-1]):          # the shared -> shared levels and the level-0 store (the last level is contiguous)
+            m = n // r
+            assert m % 8 == 0 and n % 16 == 0
+            for v in range(sx // r):
+                blk, j = divmod(v, m)
+                row0 = blk * n + j
+                for q in range(r):
+                    assert xspad(row0 + m * q) == xspad(row0) + m * q + ((m * q) >> 4), (sx, lv, v, q)
+            n //= r
+        rl = rad[-1]
+        for v0 in range(0, sx // rl, 16):          # innermost level: lane v reads elements v*RL + q
+            for q in range(rl):
+                banks = {xspad(v * rl + q) % 16 for v in range(v0, v0 + 16)}
+                assert len(banks) == 16, (sx, v0, q)
+        for i0 in range(0, sx, 16):                # consecutive elements (outer levels, untangle)
+            assert len({xspad(i) % 16 for i in range(i0, i0 + 16)}) == 16
