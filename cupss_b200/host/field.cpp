@@ -68,6 +68,16 @@ void field::copyHostToDevice() { if (system_p) system_p->uploadHostMirror(this);
 void field::copyRealHostToDevice() { if (system_p) system_p->uploadHostMirror(this); }
 void field::copyDeviceToHost() { if (system_p) system_p->refreshHostMirror(this, true, true); }
 void field::copyRealDeviceToHost() { if (system_p) system_p->refreshHostMirror(this, true, false); }
+// field::toComp / toReal / normalize / dealias of the reference (src/field.cpp:247-298, 203-232) as user-callable entry points;
+// inside a step all four are fused into the engine's passes.
+void field::toComp() {
+    if (!system_p) return;
+    system_p->uploadHostMirror(this);
+    system_p->refreshHostMirror(this, false, true);
+}
+void field::toReal() { if (system_p) system_p->refreshHostMirror(this, true, false); }
+void field::normalize() {}
+void field::dealias() {}
 void field::prepareDevice() { for (term *t : terms) t->prepareDevice(); }
 void field::precalculateImplicit(float) { /* implicit and noise factors are evaluated in-kernel from the mode index */ }
 

@@ -55,6 +55,16 @@ class field {
 
     dim3 threads_per_block, blocks;
 
+    // The reference's own transform entry points (/root/reference/inc/cupss/field.h:121-124), for user code that calls them between
+    // steps.  The engine keeps spectra on the device and no real-space copy, so: toComp() = the spectrum becomes the forward
+    // transform of the host real array (and the Fourier mirror follows); toReal() = the host real array becomes the inverse
+    // transform of the device spectrum, already normalised -- normalize() has nothing left to do, nor has dealias() (the
+    // dealiased copy is produced inside the fused k stage).
+    void toReal();
+    void toComp();
+    void normalize();
+    void dealias();
+
     void copyHostToDevice();
     void copyDeviceToHost();
     void copyRealHostToDevice();

@@ -620,6 +620,22 @@ def test_copy_host_to_device_uploads_the_edited_array(built):
     assert np.isfinite(after).all() and rel_l2(after, edited) < 0.2
 
 
+def test_user_code_calling_the_transform_entry_points(built, tmp_path):
+    """A C++ user program against inc/cupss.h that calls field::toReal / normalize / toComp / dealias between steps
+    (public in the reference, inc/cupss/field.h:121-124; semantics in INTEGRATION.md): what it adds to the host real array
+    reaches the device spectrum through toComp() and is still there after further steps."""
+    from cupss_b200 import capi
+    src = os.path.join(ROOT, "tools", "ubench", "user_entry_check.cpp")
+    exe = str(tmp_path / "user_entry_check")
+    libdir, engdir = os.path.dirname(capi.PRODUCT_LIB), os.path.dirname(capi.ENGINE_LIB)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-w", "-I", os.path.join(ROOT, "inc"), "-I", "/usr/local/cuda/include", src,
+                        "-L", libdir, "-lcupss", "-L", engdir, "-lcupss_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                        "-Wl,-rpath," + libdir, "-Wl,-rpath," + engdir, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0 and "USER_ENTRY_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_multi_gpu_slab_partition_matches_single_gpu(built):
     import torch
     if torch.cuda.device_count() < 2:

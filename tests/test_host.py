@@ -344,6 +344,32 @@ def test_reference_examples_compile_unchanged(built, tmp_path):
         assert r.returncode == 0, (s, r.stderr[-2000:])
 
 
+def test_user_code_calling_the_transform_entry_points_links(built, tmp_path):
+    """field::toComp / toReal / normalize / dealias are public in the reference (inc/cupss/field.h:121-124) and user code may call
+    them between steps: they exist here with the semantics INTEGRATION.md states (the forwarding targets -- upload of the real
+    mirror, download of the mirrors -- are covered by the GPU tests)."""
+    from cupss_b200 import capi
+    src = tmp_path / "user.cpp"
+    src.write_text('#include <cupss.h>\n'
+                   'int main() {\n'
+                   '    evolver system(RUN_GPU, 32, 32, 1.0f, 1.0f, 0.1f, 10);\n'
+                   '    system.createField("phi", true);\n'
+                   '    system.addEquation("dt phi + q^2*phi = 0");\n'
+                   '    system.prepareProblem();\n'
+                   '    system.advanceTime();\n'
+                   '    field *f = system.fields[0];\n'
+                   '    f->toReal(); f->normalize();\n'
+                   '    f->real_array[0].x += 1.0f;\n'
+                   '    f->toComp(); f->dealias();\n'
+                   '    return 0;\n'
+                   '}\n')
+    libdir, engdir = os.path.dirname(capi.PRODUCT_LIB), os.path.dirname(capi.ENGINE_LIB)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-w", "-I", os.path.join(ROOT, "inc"), "-I", "/usr/local/cuda/include", str(src),
+                        "-L", libdir, "-lcupss", "-L", engdir, "-lcupss_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-o", str(tmp_path / "user.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
 def test_one_job_stash_xpass_padded_offsets_fold():
     """kernels_xs.cu addresses its padded lines as xspad(row0) + a compile-time offset per butterfly leg.  That is only the
     same element as xspad(row0 + M*q) if the low four bits never carry; checked here for every virtual thread of every level of
