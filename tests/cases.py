@@ -163,6 +163,14 @@ CASES = {
     "mixed3d_1024x8x8": dict(shape=(1024, 8, 8), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqzu", 0)], params=dict(l=0.5, m=0.25),
                              eqs=["dt u + 0.5*q^2*u = l*iqxu*iqzu*u + m*q^2*u*iqxu", "iqxu = iqx*u", "iqzu = iqz*u"],
                              ic=dict(u=("smooth", (1.0, 0.1, 1, 4))), steps=30, threads=0),
+    # the same class of system small enough for the float64 numpy restatement (tests/test_oracle.py pins the oracle's semantics of
+    # products of different fields shared by two term groups with an independent implementation)
+    "mixed2d_64x32": dict(shape=(64, 32, 1), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqyu", 0)], params=dict(l=0.5, m=0.25),
+                          eqs=["dt u + 0.5*q^2*u = l*iqxu*iqyu + m*q^2*u*iqxu - 0.125*q^2*iqyu^2", "iqxu = iqx*u", "iqyu = iqy*u"],
+                          ic=dict(u=("smooth", (1.0, 0.1))), steps=40),
+    "mixed3d_32x16x8": dict(shape=(32, 16, 8), dt=0.01, fields=[("u", 1), ("iqxu", 0), ("iqzu", 0)], params=dict(l=0.5, m=0.25),
+                            eqs=["dt u + 0.5*q^2*u = l*iqxu*iqzu*u + m*q^2*u*iqxu", "iqxu = iqx*u", "iqzu = iqz*u"],
+                            ic=dict(u=("smooth", (1.0, 0.1))), steps=30),
     "mixed1d_2048": dict(shape=(2048, 1, 1), dt=0.01, fields=[("u", 1), ("w", 0)], params=dict(nu=0.5),   # a single line: the pair's second line does not exist
                          eqs=["dt u + nu*q^2*u = -u*w + 0.1*q^2*w*w*u", "w = iqx*u"], ic=dict(u=("smooth", (0.5, 0.05, 1, 8))), steps=60, threads=0),
     "modelh_2048x64": dict(shape=(2048, 64, 1), dt=0.1, fields=MODELH_FIELDS, params=MODELH_PARAMS, eqs=MODELH_EQS,

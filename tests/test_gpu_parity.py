@@ -68,7 +68,7 @@ def test_reference_unit_tests_operators(built, dim, flavour):
                                   "fcb_lowpass_ch2d_64", "fcb_asym_ch3d_16", "fcb_constraint_kpz2d_32", "fcb_band_diffusion_1d_64", "fcb_band_allen_cahn_2d_64",
                                   "bc_clamp_product_64", "bc_clamp_product_1d_128", "ch2d_1024", "ch2d_64x4096", "modelh_256",
                                   "ch3d_32x1024x8", "ch3d_32x8x2048", "kpz2d_128x2048_det", "ch3d_32x64x64",
-                                  "mixed2d_2048x16", "mixed2d_1024x16", "mixed2d_4096x8", "mixed3d_1024x8x8", "modelh_2048x64", "mixed1d_2048"])
+                                  "mixed2d_2048x16", "mixed2d_1024x16", "mixed2d_4096x8", "mixed3d_1024x8x8", "modelh_2048x64", "mixed1d_2048", "mixed2d_64x32", "mixed3d_32x16x8"])
 def test_parity_with_compiled_reference(built, name):
     case = CASES[name]
     lib = ORACLE_U if case.get("oracle") == "U" else ORACLE_F

@@ -47,7 +47,7 @@ def test_shim_fft_matches_numpy(built):
     lib.cupss_shim_set_double(1)
 
 
-@pytest.mark.parametrize("name", ["ch2d_64", "modelh_32", "kpz3d_32_det", "ops3d_16"])
+@pytest.mark.parametrize("name", ["ch2d_64", "modelh_32", "kpz3d_32_det", "ops3d_16", "mixed2d_64x32", "mixed3d_32x16x8"])
 def test_numpy_restatement_matches_compiled_reference(built, name):
     """Independent float64 restatement (oracle/restatement.py) vs the compiled reference with the two one-token fixes
     (== the reference GPU kernels' semantics).  20 steps; the float32 reference sits ~1e-6 from float64."""
